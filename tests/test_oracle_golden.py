@@ -1,0 +1,82 @@
+"""The oracle against the golden vectors minted from the reference's own utils.py
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+
+from oracle import dedup as odedup
+from oracle import filters, pc2
+
+
+def test_crop_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "crop.npz"))
+    p = g["points"]
+    for case in ("roi", "frac"):
+        lo, hi = g[f"{case}_min"].tolist(), g[f"{case}_max"].tolist()
+        for backend, mode in (("numpy", filters.CROP_NUMPY), ("torch", filters.CROP_TORCH)):
+            for invert in (False, True):
+                want = g[f"{case}_{backend}_{'inv' if invert else 'fwd'}"]
+                got = filters.crop_mask(p, lo, hi, invert=invert, mode=mode)
+                assert np.array_equal(got, want), (case, backend, invert)
+    # the fractional bounds must actually separate the f64 and f32 comparisons
+    lo, hi = g["frac_min"].tolist(), g["frac_max"].tolist()
+    assert not np.array_equal(filters.crop_mask(p, lo, hi, mode=filters.CROP_NUMPY),
+                              filters.crop_mask(p, lo, hi, mode=filters.CROP_TORCH))
+
+
+def test_crop_invert_is_not_complement(golden_dir):
+    g = np.load(os.path.join(golden_dir, "crop.npz"))
+    fwd, inv = g["roi_numpy_fwd"], g["roi_numpy_inv"]
+    assert (fwd & inv).any()            # boundary points pass both
+    assert (~fwd & ~inv).any()          # NaN rows pass neither
+    o3d_inv = filters.crop_mask(g["points"], g["roi_min"].tolist(), g["roi_max"].tolist(), invert=True,
+                                mode=filters.CROP_OPEN3D)
+    assert np.array_equal(o3d_inv, ~filters.crop_mask(g["points"], g["roi_min"].tolist(),
+                                                      g["roi_max"].tolist(), mode=filters.CROP_OPEN3D))
+
+
+def test_dedup_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dedup.npz"))
+    p = g["points"]
+    assert np.array_equal(odedup.numpy_index(p), g["numpy_index"])
+    # torch compat mode: N rows, points[inverse]
+    want = g["torch_index"]
+    got = odedup.torch_compat_index(p)
+    assert got.shape == want.shape == (p.shape[0],)
+    assert np.array_equal(got, want)
+    finite = np.isfinite(p).all(axis=1)
+    assert np.array_equal(odedup.torch_compat_index_numpy(p[finite]), odedup.torch_compat_index(p[finite]))
+    # open3d mode keeps bitwise-distinct -0.0 / +0.0 rows and merges identical NaN rows
+    m = odedup.open3d_mask(p)
+    assert m[10] and m[20] and m[30] and not m[40]
+
+
+def test_convert_and_metadata_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "convert.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "metadata.json")))
+    for name in ("velodyne", "autoware", "livox", "f64xyz", "rgb"):
+        spec = meta[name]
+        dt = np.dtype({"names": [f[0] for f in spec["fields"]], "formats": [f[1] for f in spec["fields"]],
+                       "offsets": [f[2] for f in spec["fields"]], "itemsize": spec["itemsize"]})
+        arr = np.frombuffer(g[f"{name}__bytes"].tobytes(), dtype=dt)
+        m = pc2.get_pointcloud_metadata(dt.names)
+        assert m == spec["metadata"], name
+        d = pc2.convert_pointcloud_to_numpy(arr, dict(m, field_names=dt.names))
+        keys = {k.split("__")[1] for k in g.files if k.startswith(name + "__")} - {"bytes"}
+        assert set(d) == keys
+        for k in keys:
+            want = g[f"{name}__{k}"]
+            assert d[k].dtype == want.dtype and np.array_equal(d[k], want, equal_nan=True), (name, k)
+    for entry in meta["mappings"]:
+        assert pc2.get_pointcloud_metadata(entry["names"]) == entry["metadata"]
+    for entry in meta["packed"]:
+        fields, step = pc2.packed_fields(entry["names"], entry["datatypes"])
+        assert step == entry["point_step"]
+        assert [[n, o, d, 1] for (n, o, d) in fields] == entry["fields"]
+
+
+def test_rgb_helpers_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rgb.npz"))
+    assert np.array_equal(pc2.extract_rgb_from_pointcloud(g["merged_float"]), g["extracted"])
+    assert np.array_equal(g["extracted"], np.stack([g["r"], g["g"], g["b"]], 1))
