@@ -1,0 +1,136 @@
+// Shared device/host plumbing for the apc kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "apc.h"
+
+#define APC_SM_COUNT 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- context -----------------------------------------------------------------------------
+// Control block living in device memory (one per context).
+struct ApcCtrl {
+  uint32_t epoch;       // bumped once per public API call; tags decoupled look-back states
+  uint32_t err;         // sticky data-dependent error bits (see ERR_* below)
+  uint32_t counters[30];
+};
+enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
+
+#define APC_NUM_SCAN_STATES 8
+
+struct apc_ctx {
+  int device = 0;
+  uint32_t max_points = 0;
+  std::string err;
+  ApcCtrl* ctrl = nullptr;                       // device
+  uint64_t* scan_state[APC_NUM_SCAN_STATES] = {};  // device, max_tiles words each
+  uint32_t max_tiles = 0;
+  // hash tables (capacity = power of two >= 2*max_points)
+  uint32_t hash_cap = 0;
+  uint64_t* vox_keys = nullptr;     // [hash_cap] packed voxel / cell keys
+  uint32_t* vox_first = nullptr;    // [hash_cap] lowest point index per slot
+  unsigned long long* vox_acc = nullptr;  // [hash_cap*4] fixed-point sums x,y,z,i
+  uint32_t* vox_cnt = nullptr;      // [hash_cap]
+  uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
+  uint32_t* p2slot = nullptr;       // [max_points]
+  uint4* dedup_slots = nullptr;     // [hash_cap] 128-bit {xbits,ybits,zbits,idx}
+  // neighbour grid
+  uint32_t* cell_start = nullptr;   // [hash_cap]
+  uint32_t* cell_fill = nullptr;    // [hash_cap]
+  float4* sorted_pts = nullptr;     // [max_points] xyz + original index bits
+  float* knn_avg = nullptr;         // [max_points]
+  double* red_a = nullptr;          // reduction ping-pong
+  double* red_b = nullptr;
+  uint32_t* nb_count = nullptr;     // [max_points]
+  // ransac
+  double* rs_planes = nullptr;      // [max_iters*4]
+  unsigned long long* rs_scores = nullptr;  // [max_iters*2] {inliers, err}
+  double* rs_partials = nullptr;    // refit partial sums
+  uint32_t rs_max_iters = 0;
+  // pipeline ping-pong buffers
+  float4* buf_a = nullptr;
+  float4* buf_b = nullptr;
+  uint8_t* mask_a = nullptr;
+  uint32_t* idx_a = nullptr;
+  uint32_t* dev_counts = nullptr;   // [16] intermediate device counters
+};
+
+int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
+// bumps the epoch; every public entry point calls it first
+int apc_begin(apc_ctx* ctx, cudaStream_t s);
+
+#define APC_CUDA(ctx, call)                                                \
+  do {                                                                     \
+    cudaError_t _e = (call);                                               \
+    if (_e != cudaSuccess) return apc_set_error((ctx), APC_ERR_CUDA, #call, _e); \
+  } while (0)
+
+#define APC_LAUNCH_CHECK(ctx, name)                                        \
+  do {                                                                     \
+    cudaError_t _e = cudaGetLastError();                                   \
+    if (_e != cudaSuccess) return apc_set_error((ctx), APC_ERR_CUDA, name, _e); \
+  } while (0)
+
+#define APC_REQUIRE(ctx, cond, msg)                                        \
+  do {                                                                     \
+    if (!(cond)) return apc_set_error((ctx), APC_ERR_BAD_ARG, msg);        \
+  } while (0)
+
+static inline uint32_t apc_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ----------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t apc_count(const uint32_t* n_dev, uint32_t n_max) {
+  uint32_t n = n_dev ? *n_dev : n_max;
+  return n < n_max ? n : n_max;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+  return __reduce_add_sync(0xffffffffu, v);
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// streaming 128-bit load / store (inputs are read once, outputs written once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// 64-bit mix (splitmix64 finaliser) used as the hash of packed keys
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// float32 rigid/projective transform, unfused, left to right, IEEE divide by w
+// (Open3D t.PointCloud.transform; oracle/filters.py:transform)
+__device__ __forceinline__ void xform_f32(const float* __restrict__ T, float& x, float& y, float& z) {
+  float r0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+  float r1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+  float r2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+  float w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[12], x), __fmul_rn(T[13], y)), __fmul_rn(T[14], z)), T[15]);
+  x = __fdiv_rn(r0, w);
+  y = __fdiv_rn(r1, w);
+  z = __fdiv_rn(r2, w);
+}
+
+__device__ __forceinline__ bool is_nan_f(float v) { return v != v; }
+__device__ __forceinline__ bool is_inf_f(float v) { return fabsf(v) == __int_as_float(0x7f800000); }
+
+#endif  // __CUDACC__

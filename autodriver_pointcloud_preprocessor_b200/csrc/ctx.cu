@@ -1,0 +1,157 @@
+// Context lifecycle, scratch sizing, error reporting (apc.h lifecycle section).
+// Replaces the reference's per-node device/point-cloud setup (pp.py:272-280, pp.py:309).
+#include <cstdio>
+#include <cstring>
+
+#include "apc_common.cuh"
+
+static thread_local std::string g_create_error;
+
+// table resets (context creation and error recovery); defined next to the kernels that own them
+int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s);
+int apc_dedup_reset(apc_ctx* ctx, cudaStream_t s);
+int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s);
+void apc_neighbors_release(apc_ctx* ctx);
+
+static int reset_tables(apc_ctx* ctx, cudaStream_t s) {
+  int rc = apc_voxel_reset(ctx, s);
+  if (!rc) rc = apc_dedup_reset(ctx, s);
+  if (!rc) rc = apc_neighbors_reset(ctx, s);
+  return rc;
+}
+
+int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce) {
+  char buf[512];
+  if (ce != cudaSuccess)
+    snprintf(buf, sizeof(buf), "apc error %d: %s: %s", code, what, cudaGetErrorString(ce));
+  else
+    snprintf(buf, sizeof(buf), "apc error %d: %s", code, what);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+__global__ void k_begin(ApcCtrl* ctrl) {
+  if (threadIdx.x == 0) ctrl->epoch = ctrl->epoch + 1u;
+  if (threadIdx.x < 30) ctrl->counters[threadIdx.x] = 0u;
+}
+
+int apc_begin(apc_ctx* ctx, cudaStream_t s) {
+  k_begin<<<1, 32, 0, s>>>(ctx->ctrl);
+  APC_LAUNCH_CHECK(ctx, "k_begin");
+  return APC_OK;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+
+static uint32_t next_pow2(uint64_t v) {
+  uint64_t p = 1024;
+  while (p < v) p <<= 1;
+  return (uint32_t)p;
+}
+
+extern "C" int apc_version(void) { return APC_VERSION; }
+
+extern "C" uint32_t apc_ctx_max_points(const apc_ctx* ctx) { return ctx ? ctx->max_points : 0; }
+
+extern "C" const char* apc_last_error(const apc_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
+  if (!ctx) return APC_OK;
+  cudaSetDevice(ctx->device);
+  apc_neighbors_release(ctx);
+  void* ptrs[] = {ctx->ctrl, ctx->vox_keys, ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank, ctx->p2slot,
+                  ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
+                  ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
+                  ctx->mask_a, ctx->idx_a, ctx->dev_counts};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto* p : ctx->scan_state)
+    if (p) cudaFree(p);
+  delete ctx;
+  return APC_OK;
+}
+
+extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
+  if (!out) return apc_set_error(nullptr, APC_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  if (max_points == 0 || max_points > (1u << 22))
+    return apc_set_error(nullptr, APC_ERR_BAD_ARG, "max_points must be in 1..4194304");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return apc_set_error(nullptr, APC_ERR_CUDA, "cudaSetDevice", e);
+  apc_ctx* ctx = new apc_ctx();
+  ctx->device = device;
+  ctx->max_points = max_points;
+  const size_t M = max_points;
+  ctx->hash_cap = next_pow2(2ull * M);
+  const size_t C = ctx->hash_cap;
+  ctx->max_tiles = apc_div_up((uint32_t)(C > M ? C : M), 1024) + 8;
+  ctx->rs_max_iters = 4096;
+  const size_t red = C / 256 + 64;
+#define A(expr)                                                         \
+  if ((e = (expr)) != cudaSuccess) {                                    \
+    apc_set_error(nullptr, APC_ERR_CUDA, "cudaMalloc(" #expr ")", e);  \
+    apc_ctx_destroy(ctx);                                               \
+    return APC_ERR_CUDA;                                                \
+  }
+  A(dalloc(&ctx->ctrl, 1));
+  for (auto& p : ctx->scan_state) A(dalloc(&p, ctx->max_tiles));
+  A(dalloc(&ctx->vox_keys, C));
+  A(dalloc(&ctx->vox_first, C));
+  A(dalloc(&ctx->vox_acc, C * 4));
+  A(dalloc(&ctx->vox_cnt, C));
+  A(dalloc(&ctx->vox_rank, C));
+  A(dalloc(&ctx->p2slot, M));
+  A(dalloc(&ctx->dedup_slots, C));
+  A(dalloc(&ctx->cell_start, C));
+  A(dalloc(&ctx->cell_fill, C));
+  A(dalloc(&ctx->sorted_pts, M));
+  A(dalloc(&ctx->knn_avg, M));
+  A(dalloc(&ctx->red_a, red));
+  A(dalloc(&ctx->red_b, red));
+  A(dalloc(&ctx->nb_count, M));
+  A(dalloc(&ctx->rs_planes, (size_t)ctx->rs_max_iters * 4));
+  A(dalloc(&ctx->rs_scores, (size_t)ctx->rs_max_iters * 2));
+  A(dalloc(&ctx->rs_partials, (size_t)(M / 256 + 64) * 10));
+  A(dalloc(&ctx->buf_a, M));
+  A(dalloc(&ctx->buf_b, M));
+  A(dalloc(&ctx->mask_a, M));
+  A(dalloc(&ctx->idx_a, M));
+  A(dalloc(&ctx->dev_counts, 16));
+  A(cudaMemset(ctx->ctrl, 0, sizeof(ApcCtrl)));
+  for (auto& p : ctx->scan_state) A(cudaMemset(p, 0, ctx->max_tiles * sizeof(uint64_t)));
+  A(cudaMemset(ctx->dev_counts, 0, 16 * sizeof(uint32_t)));
+  if (reset_tables(ctx, 0) != APC_OK) {
+    g_create_error = ctx->err;
+    apc_ctx_destroy(ctx);
+    return APC_ERR_CUDA;
+  }
+  A(cudaDeviceSynchronize());
+#undef A
+  *out = ctx;
+  return APC_OK;
+}
+
+extern "C" int apc_check(apc_ctx* ctx, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  APC_CUDA(ctx, cudaStreamSynchronize(s));
+  uint32_t err = 0;
+  APC_CUDA(ctx, cudaMemcpy(&err, &ctx->ctrl->err, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) {
+    APC_CUDA(ctx, cudaMemset(&ctx->ctrl->err, 0, sizeof(uint32_t)));
+    // a failed insert may have left the self-cleaning tables dirty: wipe them
+    int rc = reset_tables(ctx, s);
+    if (rc) return rc;
+    APC_CUDA(ctx, cudaStreamSynchronize(s));
+    if (err & APC_DEVERR_KEY_RANGE)
+      return apc_set_error(ctx, APC_ERR_KEY_RANGE,
+                           "voxel index outside +-2^20 or coordinate magnitude >= 2^16 m (non-finite input?)");
+    return apc_set_error(ctx, APC_ERR_CAPACITY, "hash table / scratch capacity exceeded");
+  }
+  return APC_OK;
+}

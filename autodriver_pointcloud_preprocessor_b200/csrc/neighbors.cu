@@ -1,0 +1,574 @@
+// Radius and statistical outlier removal with neighbour queries served from a voxel hash.
+//
+// Replaces Open3D remove_statistical_outliers (pp.py:514-519) and
+// remove_radius_outliers (TODO at pp.py:37).  Arithmetic contract
+// (oracle/outliers.py): d2 = (dx*dx + dy*dy) + dz*dz in float32 unfused; radius test
+// d2 <= float32(r)^2 with the query point included; KNN keeps the k smallest d2 (query
+// included), averages sqrtf in ascending order sequentially; mu/sigma in float64 with the
+// adjacent-pairwise tree reduction.
+//
+// Structure: a multi-level cell grid in one open-addressing hash table.  Level l has cell
+// size c0 * 2^l; the key packs (level:4 | ix:19 | iy:19 | iz:19).  Points are counting-
+// sorted per level into cell-contiguous arrays, so a query reads its 27 neighbour cells as
+// 27 short contiguous runs.  Queries run in level-0 sorted order so the lanes of a warp
+// share cells.  Radius search uses one level with c0 = r * (1 + 2^-10); KNN climbs levels
+// until the k-th distance is covered by the 27-cell block, and the rare points that never
+// are (fewer than k points in range of the coarsest level) fall to an exact brute-force
+// kernel.  The table is cleaned by the points that own rank 0 of their cell, not by memset.
+#include "apc_scan.cuh"
+
+#define GRID_EMPTY 0xffffffffffffffffull
+#define GRID_NOSLOT 0xffffffffu
+#define KNN_LEVELS 12
+#define KNN_KMAX 64
+
+// counters[] slots used by this file (zeroed by k_begin)
+#define CTR_CURSOR 0        // [0..KNN_LEVELS) per-level scatter cursors
+#define CTR_STRAGGLERS 12
+#define CTR_BBOX 14         // 6 ordered-int floats: min xyz, max xyz
+
+struct GridDev {
+  unsigned long long* keys;  // [cap]
+  uint32_t* fill;            // [cap] points in the cell
+  uint32_t* start;           // [cap] first sorted position of the cell
+  uint32_t cap_mask;
+  uint32_t levels;
+  uint32_t* slot;            // [levels][n_max] slot of point i at level l
+  uint32_t* rank;            // [levels][n_max] arrival rank of point i inside its cell
+  float4* sorted;            // [levels][n_max] xyz + original index (bits in w)
+  float* cell;               // [levels] cell sizes (device)
+};
+
+__device__ __forceinline__ bool grid_coord(float x, float y, float z, float c, int32_t& ix, int32_t& iy, int32_t& iz) {
+  const float qx = floorf(__fdiv_rn(x, c)), qy = floorf(__fdiv_rn(y, c)), qz = floorf(__fdiv_rn(z, c));
+  const float h = 262143.0f;  // one cell of margin for the +-1 neighbour offsets
+  if (!(qx >= -h && qx < h && qy >= -h && qy < h && qz >= -h && qz < h)) return false;
+  ix = (int32_t)qx; iy = (int32_t)qy; iz = (int32_t)qz;
+  return true;
+}
+__device__ __forceinline__ uint64_t grid_key(uint32_t level, int32_t ix, int32_t iy, int32_t iz) {
+  return ((uint64_t)level << 57) | ((uint64_t)(uint32_t)(ix + 262144) << 38) |
+         ((uint64_t)(uint32_t)(iy + 262144) << 19) | (uint64_t)(uint32_t)(iz + 262144);
+}
+__device__ __forceinline__ uint32_t grid_find(const GridDev& g, uint64_t key) {
+  uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
+  for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
+    const unsigned long long k = g.keys[s];
+    if (k == key) return s;
+    if (k == GRID_EMPTY) return GRID_NOSLOT;
+    s = (s + 1) & g.cap_mask;
+  }
+  return GRID_NOSLOT;
+}
+
+// ---- build ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t level = blockIdx.y;
+  const float c = g.cell[level];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    int32_t ix, iy, iz;
+    uint32_t slot = GRID_NOSLOT, rank = 0;
+    if (grid_coord(p.x, p.y, p.z, c, ix, iy, iz)) {
+      const uint64_t key = grid_key(level, ix, iy, iz);
+      uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
+      for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
+        const unsigned long long old = atomicCAS(&g.keys[s], GRID_EMPTY, (unsigned long long)key);
+        if (old == GRID_EMPTY || old == key) { slot = s; break; }
+        s = (s + 1) & g.cap_mask;
+      }
+      if (slot == GRID_NOSLOT) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+      else rank = atomicAdd(&g.fill[slot], 1u);
+    } else {
+      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+    }
+    g.slot[(size_t)level * n_max + i] = slot;
+    g.rank[(size_t)level * n_max + i] = rank;
+  }
+}
+
+// rank-0 points reserve a contiguous run for their cell (warp-aggregated cursor bump)
+__global__ void __launch_bounds__(256)
+k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t level = blockIdx.y;
+  const uint32_t lane = lane_id();
+  const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t slot = GRID_NOSLOT, cnt = 0;
+    if (i < n) {
+      slot = g.slot[(size_t)level * n_max + i];
+      if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) cnt = g.fill[slot];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&ctrl->counters[CTR_CURSOR + level], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (cnt) g.start[slot] = base + incl - cnt;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t level = blockIdx.y;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = g.slot[(size_t)level * n_max + i];
+    if (slot == GRID_NOSLOT) continue;
+    const float4 p = pts[i];
+    g.sorted[(size_t)level * n_max + g.start[slot] + g.rank[(size_t)level * n_max + i]] =
+        make_float4(p.x, p.y, p.z, __uint_as_float(i));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_grid_clean(uint32_t n_max, const uint32_t* n_dev, GridDev g) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t level = blockIdx.y;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = g.slot[(size_t)level * n_max + i];
+    if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) {
+      g.keys[slot] = GRID_EMPTY;
+      g.fill[slot] = 0u;
+    }
+  }
+}
+
+__global__ void k_grid_reset(unsigned long long* keys, uint32_t* fill, uint32_t cap) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+    keys[s] = GRID_EMPTY;
+    fill[s] = 0u;
+  }
+}
+
+__device__ __forceinline__ float d2_f32(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---- radius query -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
+               uint8_t* __restrict__ mask, uint32_t* __restrict__ counts) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const float c = g.cell[0];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float4 q = g.sorted[j];
+    const uint32_t orig = __float_as_uint(q.w);
+    int32_t ix, iy, iz;
+    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+    uint32_t cnt = 0;
+    for (int dz = -1; dz <= 1 && (need_counts || cnt < nb_points); ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
+          if (s == GRID_NOSLOT) continue;
+          const uint32_t b = g.start[s], e = b + g.fill[s];
+          for (uint32_t t = b; t < e; ++t) {
+            const float4 p = g.sorted[t];
+            cnt += (d2_f32(q.x, q.y, q.z, p.x, p.y, p.z) <= r2) ? 1u : 0u;
+          }
+        }
+    mask[orig] = cnt >= nb_points ? 1 : 0;
+    if (counts) counts[orig] = cnt;
+  }
+}
+
+// ---- KNN query ---------------------------------------------------------------------------------
+struct TopK {
+  float best[KNN_KMAX];
+  uint32_t cnt;
+  __device__ __forceinline__ void push(float d2, uint32_t k) {
+    if (cnt < k) {
+      uint32_t j = cnt++;
+      while (j > 0 && best[j - 1] > d2) { best[j] = best[j - 1]; --j; }
+      best[j] = d2;
+    } else if (d2 < best[k - 1]) {
+      uint32_t j = k - 1;
+      while (j > 0 && best[j - 1] > d2) { best[j] = best[j - 1]; --j; }
+      best[j] = d2;
+    }
+  }
+  __device__ __forceinline__ float average(uint32_t k) const {  // sequential float32, ascending
+    float s = sqrtf(best[0]);
+    for (uint32_t j = 1; j < k; ++j) s = __fadd_rn(s, sqrtf(best[j]));
+    return __fdiv_rn(s, (float)k);
+  }
+};
+
+__global__ void __launch_bounds__(128)
+k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float* __restrict__ avg,
+            uint32_t* __restrict__ stragglers, ApcCtrl* ctrl) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t k_eff = min(k, n);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float4 q = g.sorted[j];
+    const uint32_t orig = __float_as_uint(q.w);
+    bool done = false;
+    TopK tk;
+    for (uint32_t level = 0; level < g.levels && !done; ++level) {
+      const float c = g.cell[level];
+      int32_t ix, iy, iz;
+      if (!grid_coord(q.x, q.y, q.z, c, ix, iy, iz)) continue;
+      // pass 1: are there at least k points in the 27-cell block at all?
+      uint32_t cs[27], ce[27], total = 0;
+      int t = 0;
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx, ++t) {
+            const uint32_t s = grid_find(g, grid_key(level, ix + dx, iy + dy, iz + dz));
+            if (s == GRID_NOSLOT) { cs[t] = ce[t] = 0; continue; }
+            cs[t] = g.start[s];
+            ce[t] = cs[t] + g.fill[s];
+            total += ce[t] - cs[t];
+          }
+      if (total < k_eff) continue;
+      // pass 2: exact top-k over the block
+      tk.cnt = 0;
+      const float4* sp = g.sorted + (size_t)level * n_max;
+      for (t = 0; t < 27; ++t)
+        for (uint32_t u = cs[t]; u < ce[t]; ++u) {
+          const float4 p = sp[u];
+          tk.push(d2_f32(q.x, q.y, q.z, p.x, p.y, p.z), k_eff);
+        }
+      // every point closer than ~c lies inside the block; 0.999 absorbs the rounding of floor(x/c)
+      const float safe = __fmul_rn(c, 0.999f);
+      if (tk.cnt >= k_eff && tk.best[k_eff - 1] <= __fmul_rn(safe, safe)) done = true;
+    }
+    if (done) avg[orig] = tk.average(k_eff);
+    else stragglers[atomicAdd(&ctrl->counters[CTR_STRAGGLERS], 1u)] = orig;
+  }
+}
+
+// Exact brute-force KNN for the few points the grid could not resolve: one CTA per
+// straggler, per-thread top-k over a strided scan of all points, then k rounds of
+// block-wide minimum extraction.
+__global__ void __launch_bounds__(256)
+k_knn_stragglers(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint32_t k,
+                 const uint32_t* __restrict__ stragglers, const ApcCtrl* ctrl, float* __restrict__ avg) {
+  __shared__ float s_min[8];
+  __shared__ uint32_t s_who[8];
+  __shared__ float s_sel[KNN_KMAX];
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t k_eff = min(k, n);
+  const uint32_t n_str = ctrl->counters[CTR_STRAGGLERS];
+  for (uint32_t sidx = blockIdx.x; sidx < n_str; sidx += gridDim.x) {
+    const uint32_t orig = stragglers[sidx];
+    const float4 q = pts[orig];
+    TopK tk;
+    tk.cnt = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float4 p = pts[i];
+      tk.push(d2_f32(q.x, q.y, q.z, p.x, p.y, p.z), k_eff);
+    }
+    uint32_t head = 0;
+    for (uint32_t round = 0; round < k_eff; ++round) {
+      float v = head < tk.cnt ? tk.best[head] : __int_as_float(0x7f800000);
+      uint32_t who = threadIdx.x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const uint32_t ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ov < v || (ov == v && ow < who)) { v = ov; who = ow; }
+      }
+      if (lane_id() == 0) { s_min[threadIdx.x >> 5] = v; s_who[threadIdx.x >> 5] = who; }
+      __syncthreads();
+      float bv = s_min[0];
+      uint32_t bw = s_who[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w)
+        if (s_min[w] < bv || (s_min[w] == bv && s_who[w] < bw)) { bv = s_min[w]; bw = s_who[w]; }
+      if (threadIdx.x == bw) { ++head; s_sel[round] = bv; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      float s = sqrtf(s_sel[0]);
+      for (uint32_t j = 1; j < k_eff; ++j) s = __fadd_rn(s, sqrtf(s_sel[j]));
+      avg[orig] = __fdiv_rn(s, (float)k_eff);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- float64 adjacent-pairwise tree reductions (mirrors oracle/outliers.py tree_sum) ------------
+// in[i] (i < n) -> out[b] = tree sum of the 256 consecutive elements of block b (zero padded).
+// mode 0: v = (double)avgf[i]; mode 1: v = ((double)avgf[i] - mu)^2 with mu = stats[0];
+// mode 2: v = in[i] (partial sums of a previous level).
+__global__ void __launch_bounds__(256)
+k_tree_reduce(const float* __restrict__ avgf, const double* __restrict__ in, uint32_t n_max, const uint32_t* n_dev,
+              uint32_t shift, int mode, const double* __restrict__ stats, double* __restrict__ out) {
+  __shared__ double s_w[8];
+  // number of valid inputs at this level = ceil(n / 256^shift)
+  uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t s = 0; s < shift; ++s) n = (n + 255u) >> 8;
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    if (mode == 2) v = in[i];
+    else {
+      v = (double)avgf[i];
+      if (mode == 1) { const double d = __dsub_rn(v, stats[0]); v = __dmul_rn(d, d); }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane_id() == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double a = __dadd_rn(__dadd_rn(s_w[0], s_w[1]), __dadd_rn(s_w[2], s_w[3]));
+    const double b = __dadd_rn(__dadd_rn(s_w[4], s_w[5]), __dadd_rn(s_w[6], s_w[7]));
+    out[blockIdx.x] = __dadd_rn(a, b);
+  }
+}
+
+// stats[0]=mu, [1]=sigma, [2]=threshold
+__global__ void k_stat_mu(const double* sum, uint32_t n_max, const uint32_t* n_dev, double* stats) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  stats[0] = n ? __ddiv_rn(sum[0], (double)n) : 0.0;
+}
+__global__ void k_stat_sigma(const double* sumsq, uint32_t n_max, const uint32_t* n_dev, double std_ratio, double* stats) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const double sigma = n > 1 ? sqrt(__ddiv_rn(sumsq[0], (double)(n - 1))) : 0.0;
+  stats[1] = sigma;
+  stats[2] = __dadd_rn(stats[0], __dmul_rn(std_ratio, sigma));
+}
+__global__ void k_stat_mask(const float* __restrict__ avg, uint32_t n_max, const uint32_t* n_dev,
+                            const double* __restrict__ stats, uint8_t* __restrict__ mask) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const double thr = stats[2];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    mask[i] = (n < 2 || (double)avg[i] <= thr) ? 1 : 0;
+}
+
+// ---- bounding box -> level-0 cell size -----------------------------------------------------------
+__device__ __forceinline__ int32_t f2ord(float f) { const int32_t i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int32_t i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_bbox_init(ApcCtrl* ctrl) {
+  if (threadIdx.x < 3) ctrl->counters[CTR_BBOX + threadIdx.x] = (uint32_t)0x7fffffff;
+  else if (threadIdx.x < 6) ctrl->counters[CTR_BBOX + threadIdx.x] = (uint32_t)0x80000000;
+}
+__global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, ApcCtrl* ctrl) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  int32_t lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (fabsf(v[a]) < 3.0e38f) { lo[a] = min(lo[a], f2ord(v[a])); hi[a] = max(hi[a], f2ord(v[a])); }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+    hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+    if (lane_id() == 0) {
+      atomicMin(reinterpret_cast<int32_t*>(&ctrl->counters[CTR_BBOX + a]), lo[a]);
+      atomicMax(reinterpret_cast<int32_t*>(&ctrl->counters[CTR_BBOX + 3 + a]), hi[a]);
+    }
+  }
+}
+// level sizes: c0 = hint if > 0 else max extent / 4096 (>= 1e-4), c_l = c0 * 2^l
+__global__ void k_grid_cells(const ApcCtrl* ctrl, float hint, uint32_t levels, float* cell) {
+  float c0 = hint;
+  if (!(c0 > 0.0f)) {
+    float ext = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+      const float lo = ord2f((int32_t)ctrl->counters[CTR_BBOX + a]), hi = ord2f((int32_t)ctrl->counters[CTR_BBOX + 3 + a]);
+      if (hi >= lo) ext = fmaxf(ext, hi - lo);
+    }
+    c0 = fmaxf(ext * (1.0f / 4096.0f), 1.0e-4f);
+  }
+  for (uint32_t l = 0; l < levels; ++l) { cell[l] = c0; c0 = c0 * 2.0f; }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct GridHost {
+  GridDev d{};
+  uint32_t cap = 0, n_alloc = 0;
+};
+
+struct NeighborScratch {
+  GridHost grid[2];
+  uint32_t* stragglers = nullptr;
+  double* stats = nullptr;
+};
+// one scratch set per context, keyed by pointer (contexts are few; freed at process exit)
+#include <map>
+#include <mutex>
+static std::map<apc_ctx*, NeighborScratch*> g_scratch;
+static std::mutex g_scratch_mu;
+
+static NeighborScratch* scratch_of(apc_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  auto it = g_scratch.find(ctx);
+  if (it != g_scratch.end()) return it->second;
+  auto* s = new NeighborScratch();
+  g_scratch[ctx] = s;
+  return s;
+}
+
+void apc_neighbors_release(apc_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  auto it = g_scratch.find(ctx);
+  if (it == g_scratch.end()) return;
+  NeighborScratch* s = it->second;
+  for (auto& g : s->grid) {
+    void* ptrs[] = {g.d.keys, g.d.fill, g.d.start, g.d.slot, g.d.rank, g.d.sorted, g.d.cell};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  }
+  if (s->stragglers) cudaFree(s->stragglers);
+  if (s->stats) cudaFree(s->stats);
+  delete s;
+  g_scratch.erase(it);
+}
+
+// Allocates (once) the grid for `levels` levels; must run outside stream capture.
+int apc_neighbors_prepare(apc_ctx* ctx, int which) {
+  NeighborScratch* sc = scratch_of(ctx);
+  GridHost& g = sc->grid[which];
+  if (g.d.keys) return APC_OK;
+  const uint32_t levels = which == 0 ? 1u : (uint32_t)KNN_LEVELS;
+  const size_t M = ctx->max_points;
+  uint64_t want = (uint64_t)levels * M * 4 / 3 + 1024;
+  uint64_t cap = 1024;
+  while (cap < want) cap <<= 1;
+  if (which == 0 && cap < ctx->hash_cap) cap = ctx->hash_cap;
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.keys, cap * sizeof(unsigned long long)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.fill, cap * sizeof(uint32_t)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.start, cap * sizeof(uint32_t)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.slot, (size_t)levels * M * sizeof(uint32_t)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.rank, (size_t)levels * M * sizeof(uint32_t)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.sorted, (size_t)levels * M * sizeof(float4)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.cell, 16 * sizeof(float)));
+  g.d.cap_mask = (uint32_t)cap - 1;
+  g.d.levels = levels;
+  g.cap = (uint32_t)cap;
+  k_grid_reset<<<APC_SM_COUNT * 4, 256>>>(g.d.keys, g.d.fill, (uint32_t)cap);
+  APC_LAUNCH_CHECK(ctx, "k_grid_reset");
+  if (!sc->stragglers) APC_CUDA(ctx, cudaMalloc((void**)&sc->stragglers, M * sizeof(uint32_t)));
+  if (!sc->stats) APC_CUDA(ctx, cudaMalloc((void**)&sc->stats, 8 * sizeof(double)));
+  APC_CUDA(ctx, cudaDeviceSynchronize());
+  return APC_OK;
+}
+
+int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s) {
+  NeighborScratch* sc = scratch_of(ctx);
+  for (auto& g : sc->grid)
+    if (g.d.keys) k_grid_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(g.d.keys, g.d.fill, g.cap);
+  APC_LAUNCH_CHECK(ctx, "k_grid_reset");
+  return APC_OK;
+}
+
+static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_max, const uint32_t* n_dev,
+                      float cell_hint, bool need_bbox, cudaStream_t s) {
+  const uint32_t bx = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
+  if (need_bbox) {
+    k_bbox_init<<<1, 32, 0, s>>>(ctx->ctrl);
+    k_bbox<<<bx, 256, 0, s>>>(pts, n_max, n_dev, ctx->ctrl);
+  }
+  k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
+  const dim3 grid(bx, g.d.levels);
+  k_grid_insert<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d, ctx->ctrl);
+  k_grid_assign<<<grid, 256, 0, s>>>(n_max, n_dev, g.d, ctx->ctrl);
+  k_grid_scatter<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d);
+  APC_LAUNCH_CHECK(ctx, "grid_build");
+  return APC_OK;
+}
+
+int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_points,
+                       double radius, uint8_t* out_mask, uint32_t* out_counts, cudaStream_t s) {
+  if (n_max == 0) return APC_OK;
+  APC_REQUIRE(ctx, xyzi && out_mask, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  APC_REQUIRE(ctx, nb_points >= 1 && radius > 0.0, "nb_points must be >= 1 and radius > 0");
+  int rc = apc_neighbors_prepare(ctx, 0);
+  if (rc) return rc;
+  GridHost& g = scratch_of(ctx)->grid[0];
+  const float r32 = (float)radius;
+  const float r2 = r32 * r32;                       // float32(r)^2, rounded once
+  const float cell = r32 * 1.0009765625f;           // slack so that d2 <= r2 never reaches 2 cells away
+  const float4* pts = reinterpret_cast<const float4*>(xyzi);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
+  if (rc) return rc;
+  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts);
+  const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
+  k_grid_clean<<<grid, 256, 0, s>>>(n_max, n_dev, g.d);
+  APC_LAUNCH_CHECK(ctx, "radius_outliers");
+  return APC_OK;
+}
+
+extern "C" int apc_radius_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                                   int nb_points, double radius, uint8_t* out_mask, uint32_t* out_neighbor_counts,
+                                   void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  return apc_radius_nobegin(ctx, xyzi, n_max, n_dev, nb_points, radius, out_mask, out_neighbor_counts, s);
+}
+
+int apc_statistical_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_neighbors,
+                            double std_ratio, float cell_hint, uint8_t* out_mask, float* out_avg,
+                            double* out_stats_dev, cudaStream_t s) {
+  if (n_max == 0) return APC_OK;
+  APC_REQUIRE(ctx, xyzi && out_mask, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  APC_REQUIRE(ctx, nb_neighbors >= 1 && nb_neighbors <= KNN_KMAX, "nb_neighbors must be in 1..64");
+  APC_REQUIRE(ctx, std_ratio > 0.0, "std_ratio must be > 0");
+  int rc = apc_neighbors_prepare(ctx, 1);
+  if (rc) return rc;
+  NeighborScratch* sc = scratch_of(ctx);
+  GridHost& g = sc->grid[1];
+  const float4* pts = reinterpret_cast<const float4*>(xyzi);
+  float* avg = out_avg ? out_avg : ctx->knn_avg;
+  double* stats = out_stats_dev ? out_stats_dev : sc->stats;
+  rc = grid_build(ctx, g, pts, n_max, n_dev, cell_hint, !(cell_hint > 0.0f), s);
+  if (rc) return rc;
+  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  k_knn_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
+  k_knn_stragglers<<<APC_SM_COUNT * 2, 256, 0, s>>>(pts, n_max, n_dev, (uint32_t)nb_neighbors, sc->stragglers, ctx->ctrl, avg);
+  const dim3 gridc(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), g.d.levels);
+  k_grid_clean<<<gridc, 256, 0, s>>>(n_max, n_dev, g.d);
+  // mu: tree over avg (levels of 256), then sigma over squared deviations
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t cnt = n_max, shift = 0;
+    const double* in = nullptr;
+    double* out = ctx->red_a;
+    do {
+      const uint32_t blocks = apc_div_up(cnt, 256);
+      k_tree_reduce<<<blocks, 256, 0, s>>>(avg, in, n_max, n_dev, shift, shift == 0 ? pass : 2, stats, out);
+      in = out;
+      out = (out == ctx->red_a) ? ctx->red_b : ctx->red_a;
+      cnt = blocks;
+      ++shift;
+    } while (cnt > 1);
+    if (pass == 0) k_stat_mu<<<1, 1, 0, s>>>(in, n_max, n_dev, stats);
+    else k_stat_sigma<<<1, 1, 0, s>>>(in, n_max, n_dev, std_ratio, stats);
+  }
+  const uint32_t bm = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
+  k_stat_mask<<<bm, 256, 0, s>>>(avg, n_max, n_dev, stats, out_mask);
+  APC_LAUNCH_CHECK(ctx, "statistical_outliers");
+  return APC_OK;
+}
+
+extern "C" int apc_statistical_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                                        int nb_neighbors, double std_ratio, uint8_t* out_mask, float* out_avg,
+                                        double* out_stats_dev, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  return apc_statistical_nobegin(ctx, xyzi, n_max, n_dev, nb_neighbors, std_ratio, 0.0f, out_mask, out_avg,
+                                 out_stats_dev, s);
+}

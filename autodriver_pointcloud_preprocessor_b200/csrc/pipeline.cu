@@ -1,0 +1,176 @@
+// preprocess() end to end on the device (pp.py:447-544): front end -> voxel ->
+// statistical outliers -> radius outliers -> RANSAC ground removal, chained through device
+// counters so that no stage waits for the host, plus CUDA-graph capture / replay of the
+// whole chain (one launch per scan).
+#include "apc_common.cuh"
+
+// stage entry points without the per-call epoch bump (defined in the stage files)
+int apc_frontend_nobegin(apc_ctx*, const apc_cloud_desc*, uint32_t, const apc_filter_cfg*, float*, uint32_t*, uint8_t*,
+                         uint32_t*, int, cudaStream_t);
+int apc_voxel_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, float, float*, int32_t*, uint32_t*, uint32_t*,
+                      int, cudaStream_t);
+int apc_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, const uint8_t*, int, float*, uint32_t*,
+                       uint32_t*, int, cudaStream_t);
+int apc_radius_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, uint32_t*, cudaStream_t);
+int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
+                            double*, cudaStream_t);
+int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
+                              const int32_t*, double*, uint8_t*, uint32_t*, cudaStream_t);
+int apc_neighbors_prepare(apc_ctx*, int);
+
+// dev_counts layout inside the context
+enum { DC_FILTERED = 1, DC_VOXELS = 2, DC_STAT = 3, DC_RADIUS = 4, DC_OUT = 6, DC_INFO = 8 /* 4 words */ };
+
+__global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t last, int has_vox, int has_stat,
+                                  int has_rad, int has_ground, const ApcCtrl* ctrl, uint32_t* out) {
+  out[APC_CNT_INPUT] = n_input;
+  out[APC_CNT_FILTERED] = dc[DC_FILTERED];
+  uint32_t cur = dc[DC_FILTERED];
+  out[APC_CNT_VOXELS] = cur = has_vox ? dc[DC_VOXELS] : cur;
+  out[APC_CNT_AFTER_STAT] = cur = has_stat ? dc[DC_STAT] : cur;
+  out[APC_CNT_AFTER_RADIUS] = cur = has_rad ? dc[DC_RADIUS] : cur;
+  out[APC_CNT_GROUND_INLIERS] = has_ground ? dc[DC_INFO + 1] : 0u;
+  out[APC_CNT_OUTPUT] = dc[last];
+  out[APC_CNT_STATUS] = ctrl->err;
+}
+
+static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds, const apc_pipeline_cfg* cfg,
+                        float* out_xyzi, uint32_t* out_counts_dev, double* out_plane_dev, cudaStream_t s) {
+  APC_REQUIRE(ctx, clouds && cfg && out_xyzi && out_counts_dev, "NULL pointer");
+  uint32_t n_total = 0;
+  for (uint32_t i = 0; i < n_clouds && i < APC_MAX_CLOUDS; ++i) n_total += clouds[i].n_points;
+  const bool has_vox = cfg->voxel_size > 0.0f;
+  const bool has_stat = cfg->stat_enable != 0, has_rad = cfg->radius_enable != 0, has_ground = cfg->ground_enable != 0;
+  const int n_stages = 1 + has_vox + has_stat + has_rad + has_ground;
+  int rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  uint32_t* dc = ctx->dev_counts;
+  float* ping = reinterpret_cast<float*>(ctx->buf_a);
+  float* pong = reinterpret_cast<float*>(ctx->buf_b);
+  int stage = 0;
+  auto dst = [&](void) -> float* {  // output buffer of the stage about to run
+    ++stage;
+    if (stage == n_stages) return out_xyzi;
+    float* d = ping;
+    ping = pong;
+    pong = d;
+    return d;
+  };
+  float* cur = dst();
+  uint32_t cur_cnt = DC_FILTERED;
+  rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, nullptr, nullptr, dc + DC_FILTERED, 0, s);
+  if (rc) return rc;
+  if (has_vox) {
+    float* out = dst();
+    rc = apc_voxel_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->voxel_size, out, nullptr, nullptr, dc + DC_VOXELS, 1, s);
+    if (rc) return rc;
+    cur = out;
+    cur_cnt = DC_VOXELS;
+  }
+  if (has_stat) {
+    float* out = dst();
+    const float hint = has_vox ? 2.0f * cfg->voxel_size : 0.0f;
+    rc = apc_statistical_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->stat_nb_neighbors, cfg->stat_std_ratio, hint,
+                                 ctx->mask_a, nullptr, nullptr, s);
+    if (rc) return rc;
+    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, nullptr, dc + DC_STAT, 2, s);
+    if (rc) return rc;
+    cur = out;
+    cur_cnt = DC_STAT;
+  }
+  if (has_rad) {
+    float* out = dst();
+    rc = apc_radius_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
+                            ctx->mask_a, nullptr, s);
+    if (rc) return rc;
+    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, nullptr, dc + DC_RADIUS, 3, s);
+    if (rc) return rc;
+    cur = out;
+    cur_cnt = DC_RADIUS;
+  }
+  if (has_ground) {
+    float* out = dst();
+    double* plane = out_plane_dev ? out_plane_dev : ctx->red_b;
+    rc = apc_segment_plane_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->ground_distance_threshold, cfg->ground_ransac_n,
+                                   cfg->ground_num_iterations, cfg->ground_probability, cfg->ground_seed, nullptr, plane,
+                                   ctx->mask_a, dc + DC_INFO, s);
+    if (rc) return rc;
+    // pp.py:542 select_by_index(inliers, invert=True): keep the non-ground points in order
+    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 1, out, nullptr, dc + DC_OUT, 4, s);
+    if (rc) return rc;
+    cur = out;
+    cur_cnt = DC_OUT;
+  }
+  k_pipeline_counts<<<1, 1, 0, s>>>(dc, n_total, cur_cnt, has_vox, has_stat, has_rad, has_ground, ctx->ctrl, out_counts_dev);
+  APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
+  return APC_OK;
+}
+
+static int prepare(apc_ctx* ctx, const apc_pipeline_cfg* cfg) {
+  int rc = APC_OK;
+  if (cfg->radius_enable) rc = apc_neighbors_prepare(ctx, 0);
+  if (!rc && cfg->stat_enable) rc = apc_neighbors_prepare(ctx, 1);
+  return rc;
+}
+
+extern "C" int apc_pipeline_run(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                double* out_plane_dev, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, cfg, "cfg is NULL");
+  int rc = prepare(ctx, cfg);
+  if (rc) return rc;
+  return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream);
+}
+
+struct apc_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
+};
+
+extern "C" int apc_graph_destroy(apc_graph* g) {
+  if (!g) return APC_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->capture_stream) cudaStreamDestroy(g->capture_stream);
+  delete g;
+  return APC_OK;
+}
+
+extern "C" int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                          const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                          double* out_plane_dev, apc_graph** out_graph) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, cfg && out_graph, "NULL pointer");
+  *out_graph = nullptr;
+  APC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = prepare(ctx, cfg);
+  if (rc) return rc;
+  apc_graph* g = new apc_graph();
+  cudaError_t e = cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete g; return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamCreate", e); }
+  // one eager run first: lazily configured attributes (dynamic shared memory limits) are set
+  // outside the capture, and argument errors surface before a capture is open
+  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream);
+  if (!rc && (e = cudaStreamSynchronize(g->capture_stream)) != cudaSuccess)
+    rc = apc_set_error(ctx, APC_ERR_CUDA, "pipeline warm-up before capture", e);
+  if (rc) { apc_graph_destroy(g); return rc; }
+  e = cudaStreamBeginCapture(g->capture_stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { apc_graph_destroy(g); return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamBeginCapture", e); }
+  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream);
+  e = cudaStreamEndCapture(g->capture_stream, &g->graph);
+  if (rc) { apc_graph_destroy(g); return rc; }
+  if (e != cudaSuccess) { apc_graph_destroy(g); return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamEndCapture", e); }
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) { apc_graph_destroy(g); return apc_set_error(ctx, APC_ERR_CUDA, "cudaGraphInstantiate", e); }
+  *out_graph = g;
+  return APC_OK;
+}
+
+extern "C" int apc_graph_launch(apc_ctx* ctx, apc_graph* g, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, g && g->exec, "graph is NULL");
+  APC_CUDA(ctx, cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  return APC_OK;
+}

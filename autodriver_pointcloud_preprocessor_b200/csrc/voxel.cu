@@ -1,0 +1,222 @@
+// Voxel-grid mean downsampling on packed 63-bit voxel keys.
+//
+// Replaces Open3D t.PointCloud.voxel_down_sample (pp.py:509-512).
+//   key       = floor(float32(x) / float32(voxel_size)) per axis, 21 bits each (+2^20 bias)
+//   table     = open addressing, linear probing, 64-bit atomicCAS on the key word
+//   centroid  = order-independent fixed-point sums (rint(x*2^24), 64-bit integer atomics) so
+//               the result is deterministic and bit-identical to oracle/voxel.py
+//               centroids_fixed whatever order the atomics land in
+//   order     = first-occurrence: a point is "first" when it holds the lowest index of its
+//               slot; an order-preserving scan over the first-flags numbers the voxels
+// The table is self-cleaning: the thread that finalises a voxel resets its slot, so no
+// per-frame memset of the (capacity x 52 B) table sits on the critical path.
+#include "apc_scan.cuh"
+
+#define VOX_EMPTY 0xffffffffffffffffull
+#define VOX_NOSLOT 0xffffffffu
+
+__device__ __forceinline__ bool voxel_key(float4 p, float vs, uint64_t& key) {
+  const float lim = 65536.0f;
+  if (!(fabsf(p.x) < lim && fabsf(p.y) < lim && fabsf(p.z) < lim)) return false;  // also rejects NaN
+  const float qx = floorf(__fdiv_rn(p.x, vs)), qy = floorf(__fdiv_rn(p.y, vs)), qz = floorf(__fdiv_rn(p.z, vs));
+  const float h = 1048576.0f;
+  if (!(qx >= -h && qx < h && qy >= -h && qy < h && qz >= -h && qz < h)) return false;
+  const uint64_t ux = (uint64_t)((int64_t)qx + 1048576), uy = (uint64_t)((int64_t)qy + 1048576),
+                 uz = (uint64_t)((int64_t)qz + 1048576);
+  key = (ux << 42) | (uy << 21) | uz;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
+               unsigned long long* __restrict__ keys, uint32_t* __restrict__ first,
+               unsigned long long* __restrict__ acc, uint32_t* __restrict__ cnt, uint32_t cap_mask,
+               uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    uint64_t key;
+    if (!voxel_key(p, vs, key)) {
+      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+      p2slot[i] = VOX_NOSLOT;
+      continue;
+    }
+    uint32_t slot = (uint32_t)mix64(key) & cap_mask;
+    bool found = false;
+    for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
+      const unsigned long long old = atomicCAS(&keys[slot], VOX_EMPTY, (unsigned long long)key);
+      if (old == VOX_EMPTY || old == key) { found = true; break; }
+      slot = (slot + 1) & cap_mask;
+    }
+    if (!found) {
+      atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+      p2slot[i] = VOX_NOSLOT;
+      continue;
+    }
+    p2slot[i] = slot;
+    atomicMin(&first[slot], i);
+    atomicAdd(&cnt[slot], 1u);
+    // rint(x * 2^24): exact product in float64, round-half-even like numpy.rint
+    atomicAdd(&acc[4 * (size_t)slot + 0], (unsigned long long)__double2ll_rn((double)p.x * 16777216.0));
+    atomicAdd(&acc[4 * (size_t)slot + 1], (unsigned long long)__double2ll_rn((double)p.y * 16777216.0));
+    atomicAdd(&acc[4 * (size_t)slot + 2], (unsigned long long)__double2ll_rn((double)p.z * 16777216.0));
+    long long qi = 0;
+    if (fabsf(p.w) < 1048576.0f) qi = __double2ll_rn((double)p.w * 1048576.0);
+    else atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+    atomicAdd(&acc[4 * (size_t)slot + 3], (unsigned long long)qi);
+  }
+}
+
+__device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, double inv_scale) {
+  return __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sum), cnt), inv_scale));
+}
+
+__global__ void __launch_bounds__(APC_TILE_THREADS)
+k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
+                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ first,
+                 unsigned long long* __restrict__ acc, uint32_t* __restrict__ cnt, uint32_t* __restrict__ rank_of_slot,
+                 float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
+                 uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles) {
+  __shared__ uint32_t sm_scan[34];
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t epoch = ctrl->epoch;
+  const uint32_t tile = blockIdx.x;
+  bool is_first[APC_TILE_ITEMS];
+  uint32_t slot[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    is_first[j] = false;
+    slot[j] = VOX_NOSLOT;
+    if (i < n) {
+      slot[j] = p2slot[i];
+      if (slot[j] != VOX_NOSLOT) is_first[j] = (first[slot[j]] == i);
+    }
+  }
+  uint32_t rank[APC_TILE_ITEMS];
+  const uint32_t base = tile_compact_offsets(is_first, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    if (is_first[j]) {
+      const uint32_t s = slot[j];
+      const uint32_t r = base + rank[j];
+      const uint32_t c = cnt[s];
+      const double dc = (double)c;
+      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&acc[4 * (size_t)s]);
+      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&acc[4 * (size_t)s + 2]);
+      out[r] = make_float4(fixed_mean(a01.x, dc, 1.0 / 16777216.0), fixed_mean(a01.y, dc, 1.0 / 16777216.0),
+                           fixed_mean(a23.x, dc, 1.0 / 16777216.0), fixed_mean(a23.y, dc, 1.0 / 1048576.0));
+      if (out_counts) out_counts[r] = c;
+      rank_of_slot[s] = r;
+      // self-clean the slot for the next frame
+      keys[s] = VOX_EMPTY;
+      first[s] = 0xffffffffu;
+      cnt[s] = 0u;
+      *reinterpret_cast<ulonglong2*>(&acc[4 * (size_t)s]) = make_ulonglong2(0ull, 0ull);
+      *reinterpret_cast<ulonglong2*>(&acc[4 * (size_t)s + 2]) = make_ulonglong2(0ull, 0ull);
+    }
+  }
+}
+
+__global__ void k_voxel_p2v(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
+                            const uint32_t* __restrict__ rank_of_slot, int32_t* __restrict__ p2v) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = p2slot[i];
+    p2v[i] = (s == VOX_NOSLOT) ? -1 : (int32_t)rank_of_slot[s];
+  }
+}
+
+// Whole-table reset (context creation and error recovery only).
+__global__ void k_voxel_reset(unsigned long long* keys, uint32_t* first, unsigned long long* acc, uint32_t* cnt,
+                              uint32_t cap) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+    keys[s] = VOX_EMPTY;
+    first[s] = 0xffffffffu;
+    cnt[s] = 0u;
+    acc[4 * (size_t)s + 0] = 0; acc[4 * (size_t)s + 1] = 0; acc[4 * (size_t)s + 2] = 0; acc[4 * (size_t)s + 3] = 0;
+  }
+}
+
+int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s) {
+  k_voxel_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
+                                                 ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap);
+  APC_LAUNCH_CHECK(ctx, "k_voxel_reset");
+  return APC_OK;
+}
+
+int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, float voxel_size,
+                      float* out_xyzi, int32_t* out_p2v, uint32_t* out_voxel_counts, uint32_t* out_count_dev,
+                      int scan_slot, cudaStream_t s) {
+  APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
+  APC_REQUIRE(ctx, voxel_size > 0.0f, "voxel_size must be > 0");
+  if (n_max == 0) {
+    APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
+    return APC_OK;
+  }
+  APC_REQUIRE(ctx, xyzi && out_xyzi, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
+  k_voxel_insert<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size,
+                                        reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
+                                        ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
+  APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
+  const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
+  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(n_max, n_dev, ctx->p2slot,
+                                                        reinterpret_cast<unsigned long long*>(ctx->vox_keys),
+                                                        ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank,
+                                                        reinterpret_cast<float4*>(out_xyzi), out_voxel_counts,
+                                                        out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
+  APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
+  if (out_p2v) {
+    k_voxel_p2v<<<blocks, 256, 0, s>>>(n_max, n_dev, ctx->p2slot, ctx->vox_rank, out_p2v);
+    APC_LAUNCH_CHECK(ctx, "k_voxel_p2v");
+  }
+  return APC_OK;
+}
+
+extern "C" int apc_voxel_downsample(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                                    float voxel_size, float* out_xyzi, int32_t* out_p2v,
+                                    uint32_t* out_voxel_counts, uint32_t* out_count_dev, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  return apc_voxel_nobegin(ctx, xyzi, n_max, n_dev, voxel_size, out_xyzi, out_p2v, out_voxel_counts, out_count_dev, 1, s);
+}
+
+// Per-attribute voxel mean, Open3D style: float32 sums (atomics), then sum / count in float32.
+__global__ void k_attr_zero(uint32_t n_max, const uint32_t* n_vox, float* sum, float* cnt) {
+  const uint32_t n = apc_count(n_vox, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { sum[i] = 0.f; cnt[i] = 0.f; }
+}
+__global__ void k_attr_add(const float* __restrict__ attr, const int32_t* __restrict__ p2v, uint32_t n_max,
+                           const uint32_t* n_dev, float* sum, float* cnt) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t v = p2v[i];
+    if (v >= 0) { atomicAdd(&sum[v], attr[i]); atomicAdd(&cnt[v], 1.0f); }
+  }
+}
+__global__ void k_attr_div(uint32_t n_max, const uint32_t* n_vox, const float* __restrict__ sum,
+                           const float* __restrict__ cnt, float* __restrict__ out) {
+  const uint32_t n = apc_count(n_vox, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = __fdiv_rn(sum[i], cnt[i]);
+}
+
+extern "C" int apc_voxel_mean_attr(apc_ctx* ctx, const float* attr, const int32_t* p2v, uint32_t n_max,
+                                   const uint32_t* n_dev, const uint32_t* n_voxels_dev, float* out_attr, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  if (n_max == 0) return APC_OK;
+  APC_REQUIRE(ctx, attr && p2v && out_attr, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* sum = ctx->knn_avg;                               // scratch reuse: [max_points] floats each
+  float* cnt = reinterpret_cast<float*>(ctx->nb_count);
+  const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
+  k_attr_zero<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, sum, cnt);
+  k_attr_add<<<blocks, 256, 0, s>>>(attr, p2v, n_max, n_dev, sum, cnt);
+  k_attr_div<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, sum, cnt, out_attr);
+  APC_LAUNCH_CHECK(ctx, "k_attr_*");
+  return APC_OK;
+}

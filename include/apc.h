@@ -1,0 +1,273 @@
+/*
+ * apc.h - C ABI of the B200-native per-scan point-cloud preprocessing hot path.
+ *
+ * "apc" = autodriver point cloud.  This is the drop-in boundary: plain C types, device
+ * pointers and sizes, no torch / Open3D types, no exceptions.  Each entry point replaces a
+ * call the reference (privvyledge/autodriver_pointcloud_preprocessor, all Python) makes
+ * into numpy / torch / Open3D / sensor_msgs_py; the replaced call site is cited on every
+ * declaration as <file>:<line> relative to the reference root, with
+ *   pp.py    = autodriver_pointcloud_preprocessor/pointcloud_preprocessor.py
+ *   utils.py = autodriver_pointcloud_preprocessor/utils.py
+ *   concat.py= autodriver_pointcloud_preprocessor/pointcloud_concatenator.py
+ * The Python binding a maintainer adds on the reference side is ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the
+ *     caller (a torch tensor in the Python host code); the context owns only scratch.
+ *   - point clouds are SoA: `xyzi` is float4[N] = (x, y, z, intensity) per point, 16-byte
+ *     aligned; other attributes travel as separate arrays gathered with apc_gather /
+ *     averaged with apc_voxel_mean_attr.
+ *   - variable-size results never force a host sync: a stage takes its input size as
+ *     `n_max` (host upper bound, sizes the grid) plus an optional device counter `n_dev`
+ *     (when non-NULL the kernels read the true size from it) and writes its output size to
+ *     a device counter.  Output buffers must hold `n_max` elements.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
+ *     asynchronous; a context is bound to one device and must be used from one thread /
+ *     stream at a time (the reference runs one callback at a time, pp.py:1056).
+ *   - return value: APC_OK or a negative apc_status; apc_last_error(ctx) gives the text.
+ *     Data-dependent failures (key range, table capacity) are raised on the device and
+ *     reported by apc_check(ctx) after the stream has been synchronised.
+ */
+#ifndef APC_H_
+#define APC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APC_VERSION 100 /* 0.1.0 */
+
+typedef enum apc_status {
+  APC_OK = 0,
+  APC_ERR_CUDA = -1,       /* a CUDA runtime call failed */
+  APC_ERR_BAD_ARG = -2,    /* NULL pointer, size over the context limit, bad enum ... */
+  APC_ERR_KEY_RANGE = -3,  /* voxel index outside +-2^20 or |coordinate| >= 2^16 m */
+  APC_ERR_CAPACITY = -4,   /* hash table / scratch too small for this input */
+  APC_ERR_TOO_FEW = -5     /* fewer points than ransac_n (segment_plane) */
+} apc_status;
+
+/* sensor_msgs/PointField datatype codes (utils.py:28-37 FIELD_DTYPE_MAP) */
+enum { APC_INT8 = 1, APC_UINT8 = 2, APC_INT16 = 3, APC_UINT16 = 4, APC_INT32 = 5,
+       APC_UINT32 = 6, APC_FLOAT32 = 7, APC_FLOAT64 = 8 };
+
+#define APC_MAX_FIELDS 16     /* fields read_points may test for NaN */
+#define APC_MAX_CLOUDS 8      /* sensors merged in one launch */
+#define APC_MAX_TRANSFORMS 3  /* offset(lidar) -> TF -> offset(robot), pp.py:480-491 */
+
+typedef struct apc_field {
+  int32_t offset;   /* byte offset inside a point record */
+  int32_t datatype; /* APC_INT8 .. APC_FLOAT64; 0 = field absent */
+} apc_field;
+
+/* One PointCloud2 byte buffer (= one sensor).  Mirrors the message attributes read by
+ * read_points (utils.py:206-211) and convert_pointcloud_to_numpy (utils.py:102-131). */
+typedef struct apc_cloud_desc {
+  const void* data_dev;   /* device: width*height*point_step bytes */
+  uint32_t n_points;      /* width*height */
+  uint32_t point_step;
+  apc_field x, y, z;      /* any numeric datatype; cast to float32 like .astype(np.float32) */
+  apc_field intensity;    /* datatype 0 -> intensity 0.0f */
+  uint32_t n_nan_fields;  /* read_points NaN test: every selected field; ints never NaN */
+  apc_field nan_fields[APC_MAX_FIELDS];
+  int32_t has_transform;  /* per-sensor extrinsic applied before the common transforms */
+  float transform[16];    /* row-major float32 4x4 (concat.py:1-5 "transform to a target frame") */
+} apc_cloud_desc;
+
+/* crop back ends, utils.py:254,272,298 */
+enum { APC_CROP_NUMPY = 0,  /* float64 compare; invert = any(p<=min | p>=max) */
+       APC_CROP_TORCH = 1,  /* float32 compare; invert as numpy */
+       APC_CROP_OPEN3D = 2  /* float32 inclusive; invert = logical NOT */ };
+
+/* duplicate-removal back ends, utils.py:520,535,543 */
+enum { APC_DEDUP_OFF = 0,
+       APC_DEDUP_OPEN3D = 1 /* bit-pattern key, lowest index kept, order preserved */ };
+
+typedef struct apc_filter_cfg {
+  int32_t skip_nans;      /* read_points: (skip_nans && !is_dense), utils.py:209 */
+  int32_t dedup_mode;     /* APC_DEDUP_* , pp.py:450-463 */
+  int32_t remove_nan;     /* pp.py:469-471 */
+  int32_t remove_inf;
+  uint32_t n_transforms;  /* applied back to back, each rounded to float32 (pp.py:480-491) */
+  float transforms[APC_MAX_TRANSFORMS][16];
+  int32_t crop_enable;    /* pp.py:494-506 */
+  int32_t crop_mode;      /* APC_CROP_* */
+  int32_t crop_invert;
+  double roi_min[3];
+  double roi_max[3];
+} apc_filter_cfg;
+
+/* bits of the optional per-input-point stage mask written by apc_frontend */
+enum { APC_STAGE_NANSKIP = 1, APC_STAGE_DEDUP = 2, APC_STAGE_FINITE = 4, APC_STAGE_CROP = 8 };
+
+typedef struct apc_ctx apc_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+
+/* Creates a context on `device` with scratch for clouds of up to `max_points` points
+ * (sum over sensors).  Replaces the reference's per-node Open3D device/point-cloud setup
+ * (pp.py:272-280, pp.py:309). */
+int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out);
+int apc_ctx_destroy(apc_ctx* ctx);
+/* text of the last error recorded on this context ("" if none); ctx may be NULL for
+ * errors raised by apc_ctx_create */
+const char* apc_last_error(const apc_ctx* ctx);
+/* Synchronises `stream`, then reports (and clears) data-dependent device-side errors of
+ * the calls issued since the previous check: APC_OK / APC_ERR_KEY_RANGE / APC_ERR_CAPACITY. */
+int apc_check(apc_ctx* ctx, void* stream);
+int apc_version(void);
+uint32_t apc_ctx_max_points(const apc_ctx* ctx);
+
+/* ---- (1)+(2)+(6) unpack, transform, filter, compact, concat --------------------- */
+
+/* Fused front end over 1..APC_MAX_CLOUDS PointCloud2 byte buffers, in one launch:
+ *   read_points NaN skip (utils.py:206-211) -> [duplicate removal, utils.py:509-546] ->
+ *   remove_non_finite_points (pp.py:469) -> per-sensor transform (concat.py:1-5) ->
+ *   common transforms (pp.py:482,487,490) -> crop_pointcloud (utils.py:240-301) ->
+ *   order-preserving select_by_mask (utils.py:271,297).
+ * Outputs (device, capacity = sum of n_points): out_xyzi float4[], out_src_idx uint32[]
+ * (index of each survivor in the concatenated input; NULL to skip), out_stage_mask
+ * uint8[sum n_points] (APC_STAGE_* bits per input point; NULL to skip),
+ * out_count_dev uint32[1]. */
+int apc_frontend(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                 const apc_filter_cfg* cfg, float* out_xyzi, uint32_t* out_src_idx,
+                 uint8_t* out_stage_mask, uint32_t* out_count_dev, void* stream);
+
+/* PointCloud2 bytes -> SoA float4 without filtering (utils.py:51-133 positions+intensity). */
+int apc_unpack(apc_ctx* ctx, const apc_cloud_desc* cloud, float* out_xyzi, void* stream);
+
+/* t.PointCloud.transform on an SoA cloud, in place allowed (pp.py:482,487,490). */
+int apc_transform(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                  const float* T16_host, float* out_xyzi, void* stream);
+
+/* Masks computed stand-alone for the Open3D-like carrier methods:
+ * crop (utils.py:267-299), remove_non_finite_points (pp.py:469),
+ * remove_duplicated_points (utils.py:544).  out_mask uint8[n_max], 1 = keep. */
+int apc_crop_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                  const double* roi_min, const double* roi_max, int mode, int invert,
+                  uint8_t* out_mask, void* stream);
+int apc_non_finite_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                        int remove_nan, int remove_inf, uint8_t* out_mask, void* stream);
+int apc_duplicate_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                       uint8_t* out_mask, void* stream);
+
+/* select_by_mask (utils.py:271,297; pp.py:542 with invert): order-preserving compaction.
+ * out_idx (uint32[n_max], may be NULL) receives the surviving indices. */
+int apc_select_by_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                       const uint8_t* mask, int invert, float* out_xyzi, uint32_t* out_idx,
+                       uint32_t* out_count_dev, void* stream);
+
+/* select_by_index for attribute arrays (pp.py:801 copy_fields after filtering):
+ * out[i] = src[idx[i]] for elem_size in {1,2,4,8,12,16} bytes. */
+int apc_gather(apc_ctx* ctx, const void* src, uint32_t elem_size, const uint32_t* idx,
+               uint32_t n_max, const uint32_t* n_dev, void* out, void* stream);
+
+/* ---- (3) voxel grid ---------------------------------------------------------------- */
+
+/* voxel_down_sample(voxel_size) (pp.py:509-512), mean reduction, float32 voxel index
+ * floor(x / voxel_size), output in first-occurrence order, centroids by deterministic
+ * fixed-point accumulation.  out_p2v int32[n_max] (voxel row of every input
+ * point) and out_voxel_counts uint32[n_max] may be NULL. */
+int apc_voxel_downsample(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                         float voxel_size, float* out_xyzi, int32_t* out_p2v,
+                         uint32_t* out_voxel_counts, uint32_t* out_count_dev, void* stream);
+
+/* Per-attribute voxel mean "in float32 then cast back" (Open3D index_add per attribute,
+ * SURVEY.md B7) for a float32 attribute, using p2v / counts from apc_voxel_downsample. */
+int apc_voxel_mean_attr(apc_ctx* ctx, const float* attr, const int32_t* p2v, uint32_t n_max,
+                        const uint32_t* n_dev, const uint32_t* n_voxels_dev, float* out_attr,
+                        void* stream);
+
+/* ---- (5) outlier removal ----------------------------------------------------------- */
+
+/* remove_radius_outliers(nb_points, search_radius) (TODO at pp.py:37; Open3D semantics):
+ * keep iff #{j : d2(i,j) <= r^2, self included} >= nb_points.  out_mask uint8[n_max];
+ * out_neighbor_counts uint32[n_max] may be NULL. */
+int apc_radius_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                        int nb_points, double radius, uint8_t* out_mask,
+                        uint32_t* out_neighbor_counts, void* stream);
+
+/* remove_statistical_outliers(nb_neighbors, std_ratio) (pp.py:514-519).  out_avg
+ * float32[n_max] (mean distance to the k nearest, self included) may be NULL;
+ * out_stats_dev double[3] = (mu, sigma, threshold) may be NULL. */
+int apc_statistical_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_max,
+                             const uint32_t* n_dev, int nb_neighbors, double std_ratio,
+                             uint8_t* out_mask, float* out_avg, double* out_stats_dev,
+                             void* stream);
+
+/* ---- (4) RANSAC ground plane --------------------------------------------------------- */
+
+/* segment_plane(distance_threshold, ransac_n, num_iterations, probability) (pp.py:533-543).
+ * Hypotheses come from the counter-based generator seeded with `seed`, or from
+ * `sample_table_dev` (int32[num_iterations*ransac_n], device) when non-NULL.
+ * out_plane_dev double[8]: [0..3] least-squares refit on the final inliers (the returned
+ * plane_model), [4..7] the winning hypothesis.  out_inlier_mask uint8[n_max] (1 = inlier).
+ * out_info_dev uint32[4]: {best_iteration or 0xFFFFFFFF, n_inliers, 0, 0}. */
+int apc_segment_plane(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                      double distance_threshold, int ransac_n, int num_iterations,
+                      double probability, uint64_t seed, const int32_t* sample_table_dev,
+                      double* out_plane_dev, uint8_t* out_inlier_mask, uint32_t* out_info_dev,
+                      void* stream);
+
+/* ---- (1 inverse) repack to PointCloud2 bytes ------------------------------------------ */
+
+typedef struct apc_out_field {
+  int32_t offset;    /* byte offset in the packed output record (utils.py:152-163) */
+  int32_t datatype;  /* APC_* */
+  int32_t source;    /* 0 = zeros, 1 = x, 2 = y, 3 = z, 4 = intensity, 5 = extra attr array */
+  int32_t attr_datatype; /* source 5: APC_* element type of attr_dev */
+  const void* attr_dev;  /* source 5: device array [n_max] holding the attribute values */
+} apc_out_field;
+
+/* prepare_pointcloud + create_cloud (pp.py:576-625, pp.py:769): write the surviving points
+ * into the packed output layout; fields without a source are zeros (pp.py:593). */
+int apc_repack(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+               const apc_out_field* fields, uint32_t n_fields, uint32_t point_step,
+               uint8_t* out_bytes, void* stream);
+
+/* ---- whole per-scan pipeline ----------------------------------------------------------- */
+
+typedef struct apc_pipeline_cfg {
+  apc_filter_cfg filter;
+  float voxel_size;            /* <= 0 disables (pp.py:509) */
+  int32_t stat_enable;         /* pp.py:514 */
+  int32_t stat_nb_neighbors;
+  double stat_std_ratio;
+  int32_t radius_enable;       /* additive stage, TODO pp.py:37 */
+  int32_t radius_nb_points;
+  double radius_search_radius;
+  int32_t ground_enable;       /* pp.py:533 */
+  double ground_distance_threshold;
+  int32_t ground_ransac_n;
+  int32_t ground_num_iterations;
+  double ground_probability;
+  uint64_t ground_seed;
+} apc_pipeline_cfg;
+
+/* counters mirrored to the host after a pipeline run (index into out_counts_dev uint32[8]) */
+enum { APC_CNT_INPUT = 0, APC_CNT_FILTERED = 1, APC_CNT_VOXELS = 2, APC_CNT_AFTER_STAT = 3,
+       APC_CNT_AFTER_RADIUS = 4, APC_CNT_GROUND_INLIERS = 5, APC_CNT_OUTPUT = 6, APC_CNT_STATUS = 7 };
+
+/* preprocess() (pp.py:447-544) end to end on the device: front end -> voxel -> statistical
+ * -> radius -> RANSAC ground removal, no host synchronisation.  out_xyzi float4[sum
+ * n_points]; out_counts_dev uint32[8] (APC_CNT_*); out_plane_dev double[8] (may be NULL). */
+int apc_pipeline_run(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                     const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                     double* out_plane_dev, void* stream);
+
+/* The same pipeline captured once into a CUDA graph (fixed buffers, sizes and config) and
+ * replayed per scan: one launch per frame instead of ~25.  The per-frame input is whatever
+ * the captured data_dev buffers hold when apc_graph_launch runs. */
+typedef struct apc_graph apc_graph;
+int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                               const apc_pipeline_cfg* cfg, float* out_xyzi,
+                               uint32_t* out_counts_dev, double* out_plane_dev,
+                               apc_graph** out_graph);
+int apc_graph_launch(apc_ctx* ctx, apc_graph* graph, void* stream);
+int apc_graph_destroy(apc_graph* graph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APC_H_ */
