@@ -292,8 +292,9 @@ static int build_params(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
 }
 
 static int set_smem(apc_ctx* ctx, uint32_t smem) {
-  static uint32_t configured = 0;  // both kernels share the limit; raise monotonically
-  if (smem > 48 * 1024 && smem > configured) {
+  static uint32_t configured = 0;  // both kernels share the limit; opt in once
+  // static shared memory counts against the 48 KB default too, so opt in well below it
+  if (smem > 32 * 1024 && smem > configured) {
     APC_CUDA(ctx, cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
     APC_CUDA(ctx, cudaFuncSetAttribute(k_dedup_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
     configured = 192 * 1024;

@@ -133,7 +133,7 @@ extern "C" int apc_repack(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const
   prm.step = point_step;
   const uint32_t smem = APC_TILE_POINTS * point_step + 16;
   static bool configured = false;
-  if (smem > 48 * 1024 && !configured) {
+  if (smem > 32 * 1024 && !configured) {
     APC_CUDA(ctx, cudaFuncSetAttribute(k_repack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
