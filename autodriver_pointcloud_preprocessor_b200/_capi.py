@@ -89,6 +89,9 @@ def _load():
                                        C.POINTER(vp)],
         "apc_graph_launch": [vp, vp, vp],
         "apc_graph_destroy": [vp],
+        "apc_graph_kernel_count": [vp],
+        "apc_profile_enable": [vp, i32],
+        "apc_profile_report": [vp, C.c_char_p, u32],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -109,7 +112,8 @@ SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
            "apc_statistical_outliers", "apc_segment_plane", "apc_repack", "apc_pipeline_run",
-           "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy"]
+           "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",
+           "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report"]
 
 
 class ApcError(RuntimeError):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "apc.h"
 
@@ -19,7 +20,16 @@ enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
 
 #define APC_NUM_SCAN_STATES 8
 
+// Optional per-kernel timing with CUDA events on the launching stream (apc_profile_*).
+struct ApcProf {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;       // pairs: start, stop
+  std::vector<const char*> names;    // one per pair
+  size_t used = 0;                   // pairs in use
+};
+
 struct apc_ctx {
+  ApcProf prof;
   int device = 0;
   uint32_t max_points = 0;
   std::string err;
@@ -55,6 +65,34 @@ struct apc_ctx {
   uint32_t* idx_a = nullptr;
   uint32_t* dev_counts = nullptr;   // [16] intermediate device counters
 };
+
+// RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.
+struct ProfScope {
+  apc_ctx* c;
+  cudaStream_t s;
+  cudaEvent_t stop = nullptr;
+  ProfScope(apc_ctx* ctx, const char* name, cudaStream_t stream) : c(ctx), s(stream) {
+    if (!c->prof.enabled) return;
+    ApcProf& p = c->prof;
+    if (p.used * 2 + 2 > p.ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      p.ev.push_back(a);
+      p.ev.push_back(b);
+      p.names.push_back(name);
+    }
+    p.names[p.used] = name;
+    cudaEventRecord(p.ev[p.used * 2], s);
+    stop = p.ev[p.used * 2 + 1];
+    ++p.used;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, s);
+  }
+};
+#define APC_PROF_CAT2(a, b) a##b
+#define APC_PROF_CAT(a, b) APC_PROF_CAT2(a, b)
+#define APC_PROF(ctx, name, stream) ProfScope APC_PROF_CAT(_prof_, __LINE__)(ctx, name, stream)
 
 int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
 // bumps the epoch; every public entry point calls it first

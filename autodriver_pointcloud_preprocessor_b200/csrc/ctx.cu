@@ -64,6 +64,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   if (!ctx) return APC_OK;
   cudaSetDevice(ctx->device);
   apc_neighbors_release(ctx);
+  for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   void* ptrs[] = {ctx->ctrl, ctx->vox_keys, ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
@@ -134,6 +135,43 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
 #undef A
   *out = ctx;
   return APC_OK;
+}
+
+extern "C" int apc_profile_enable(apc_ctx* ctx, int on) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  ctx->prof.enabled = on != 0;
+  ctx->prof.used = 0;
+  return APC_OK;
+}
+
+extern "C" int apc_profile_report(apc_ctx* ctx, char* buf, uint32_t buf_len) {
+  if (!ctx || !buf || buf_len == 0) return APC_ERR_BAD_ARG;
+  APC_CUDA(ctx, cudaDeviceSynchronize());
+  ApcProf& p = ctx->prof;
+  std::vector<const char*> names;
+  std::vector<double> total;
+  std::vector<int> count;
+  for (size_t i = 0; i < p.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev[2 * i], p.ev[2 * i + 1]) != cudaSuccess) continue;
+    size_t k = 0;
+    for (; k < names.size(); ++k)
+      if (strcmp(names[k], p.names[i]) == 0) break;
+    if (k == names.size()) { names.push_back(p.names[i]); total.push_back(0.0); count.push_back(0); }
+    total[k] += ms;
+    count[k] += 1;
+  }
+  p.used = 0;
+  std::string out;
+  char line[160];
+  for (size_t k = 0; k < names.size(); ++k) {
+    snprintf(line, sizeof(line), "%s %.6f %d\n", names[k], total[k], count[k]);
+    out += line;
+  }
+  const size_t n = out.size() < (size_t)buf_len - 1 ? out.size() : (size_t)buf_len - 1;
+  memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  return (int)n;
 }
 
 extern "C" int apc_check(apc_ctx* ctx, void* stream) {

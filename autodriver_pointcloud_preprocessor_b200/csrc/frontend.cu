@@ -324,9 +324,11 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
   rc = set_smem(ctx, smem);
   if (rc) return rc;
   if (prm.dedup) {
+    APC_PROF(ctx, "k_dedup_insert", s);
     k_dedup_insert<<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
     APC_LAUNCH_CHECK(ctx, "k_dedup_insert");
   }
+  APC_PROF(ctx, "k_frontend", s);
   k_frontend<<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
   APC_LAUNCH_CHECK(ctx, "k_frontend");
   return APC_OK;
@@ -534,6 +536,7 @@ int apc_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   APC_REQUIRE(ctx, mask, "mask is NULL");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
+  APC_PROF(ctx, "k_select_by_mask", s);
   k_select_by_mask<<<n_tiles, APC_TILE_THREADS, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, mask, invert,
                                                         reinterpret_cast<float4*>(out_xyzi), out_idx, out_count_dev,
                                                         ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);

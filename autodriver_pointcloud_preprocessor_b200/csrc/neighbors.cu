@@ -478,8 +478,15 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
   }
   k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
   const dim3 grid(bx, g.d.levels);
-  k_grid_insert<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d, ctx->ctrl);
-  k_grid_assign<<<grid, 256, 0, s>>>(n_max, n_dev, g.d, ctx->ctrl);
+  {
+    APC_PROF(ctx, "k_grid_insert", s);
+    k_grid_insert<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d, ctx->ctrl);
+  }
+  {
+    APC_PROF(ctx, "k_grid_assign", s);
+    k_grid_assign<<<grid, 256, 0, s>>>(n_max, n_dev, g.d, ctx->ctrl);
+  }
+  APC_PROF(ctx, "k_grid_scatter", s);
   k_grid_scatter<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d);
   APC_LAUNCH_CHECK(ctx, "grid_build");
   return APC_OK;
@@ -501,8 +508,12 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
   if (rc) return rc;
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
-  k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts);
+  {
+    APC_PROF(ctx, "k_radius_query", s);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts);
+  }
   const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
+  APC_PROF(ctx, "k_grid_clean", s);
   k_grid_clean<<<grid, 256, 0, s>>>(n_max, n_dev, g.d);
   APC_LAUNCH_CHECK(ctx, "radius_outliers");
   return APC_OK;
@@ -536,10 +547,20 @@ int apc_statistical_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, con
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell_hint, !(cell_hint > 0.0f), s);
   if (rc) return rc;
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
-  k_knn_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
-  k_knn_stragglers<<<APC_SM_COUNT * 2, 256, 0, s>>>(pts, n_max, n_dev, (uint32_t)nb_neighbors, sc->stragglers, ctx->ctrl, avg);
+  {
+    APC_PROF(ctx, "k_knn_query", s);
+    k_knn_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
+  }
+  {
+    APC_PROF(ctx, "k_knn_stragglers", s);
+    k_knn_stragglers<<<APC_SM_COUNT * 2, 256, 0, s>>>(pts, n_max, n_dev, (uint32_t)nb_neighbors, sc->stragglers, ctx->ctrl, avg);
+  }
   const dim3 gridc(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), g.d.levels);
-  k_grid_clean<<<gridc, 256, 0, s>>>(n_max, n_dev, g.d);
+  {
+    APC_PROF(ctx, "k_grid_clean", s);
+    k_grid_clean<<<gridc, 256, 0, s>>>(n_max, n_dev, g.d);
+  }
+  APC_PROF(ctx, "stat_reduce_mask", s);
   // mu: tree over avg (levels of 256), then sigma over squared deviations
   for (int pass = 0; pass < 2; ++pass) {
     uint32_t cnt = n_max, shift = 0;

@@ -168,6 +168,20 @@ extern "C" int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* cl
   return APC_OK;
 }
 
+extern "C" int apc_graph_kernel_count(const apc_graph* g) {
+  if (!g || !g->graph) return APC_ERR_BAD_ARG;
+  size_t n = 0;
+  if (cudaGraphGetNodes(g->graph, nullptr, &n) != cudaSuccess) return APC_ERR_CUDA;
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n && cudaGraphGetNodes(g->graph, nodes.data(), &n) != cudaSuccess) return APC_ERR_CUDA;
+  int kernels = 0;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++kernels;
+  }
+  return kernels;
+}
+
 extern "C" int apc_graph_launch(apc_ctx* ctx, apc_graph* g, void* stream) {
   if (!ctx) return APC_ERR_BAD_ARG;
   APC_REQUIRE(ctx, g && g->exec, "graph is NULL");

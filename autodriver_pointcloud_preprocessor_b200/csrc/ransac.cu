@@ -276,13 +276,26 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   APC_REQUIRE(ctx, xyzi, "NULL pointer");
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   const double scale = 4294967296.0 / (thr * thr);
-  k_rs_hypotheses<<<apc_div_up(iters, 64), 64, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes);
-  k_rs_zero<<<apc_div_up(2 * iters, 256), 256, 0, s>>>(ctx->rs_scores, 2 * iters);
+  {
+    APC_PROF(ctx, "k_rs_hypotheses", s);
+    k_rs_hypotheses<<<apc_div_up(iters, 64), 64, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes);
+    k_rs_zero<<<apc_div_up(2 * iters, 256), 256, 0, s>>>(ctx->rs_scores, 2 * iters);
+  }
   const dim3 grid(apc_div_up(n_max, APC_TILE_POINTS), apc_div_up(iters, RS_CHUNK));
-  k_rs_score<<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ctx->rs_planes, iters, thr, scale, ctx->rs_scores);
-  k_rs_select<<<1, 1, 0, s>>>(ctx->rs_planes, ctx->rs_scores, n_max, n_dev, ransac_n, iters, prob, out_plane, out_info);
+  {
+    APC_PROF(ctx, "k_rs_score", s);
+    k_rs_score<<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ctx->rs_planes, iters, thr, scale, ctx->rs_scores);
+  }
+  {
+    APC_PROF(ctx, "k_rs_select", s);
+    k_rs_select<<<1, 1, 0, s>>>(ctx->rs_planes, ctx->rs_scores, n_max, n_dev, ransac_n, iters, prob, out_plane, out_info);
+  }
   const uint32_t fb = apc_div_up(n_max, 256);
-  k_rs_final<<<fb, 256, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials);
+  {
+    APC_PROF(ctx, "k_rs_final", s);
+    k_rs_final<<<fb, 256, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials);
+  }
+  APC_PROF(ctx, "k_rs_refit", s);
   k_rs_refit<<<1, 256, 0, s>>>(ctx->rs_partials, fb, n_max, n_dev, out_plane, out_info);
   APC_LAUNCH_CHECK(ctx, "segment_plane");
   return APC_OK;

@@ -137,6 +137,7 @@ extern "C" int apc_repack(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const
     APC_CUDA(ctx, cudaFuncSetAttribute(k_repack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
+  APC_PROF(ctx, "k_repack", (cudaStream_t)stream);
   k_repack<<<apc_div_up(n_max, APC_TILE_POINTS), APC_TILE_THREADS, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(xyzi), n_max, n_dev, prm, out_bytes);
   APC_LAUNCH_CHECK(ctx, "k_repack");

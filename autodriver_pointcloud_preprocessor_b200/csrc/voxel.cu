@@ -157,11 +157,15 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   APC_REQUIRE(ctx, xyzi && out_xyzi, "NULL pointer");
   APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
   const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
-  k_voxel_insert<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size,
-                                        reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
-                                        ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
+  {
+    APC_PROF(ctx, "k_voxel_insert", s);
+    k_voxel_insert<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size,
+                                          reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
+                                          ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
+  }
   APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
+  APC_PROF(ctx, "k_voxel_finalize", s);
   k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(n_max, n_dev, ctx->p2slot,
                                                         reinterpret_cast<unsigned long long*>(ctx->vox_keys),
                                                         ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank,

@@ -134,6 +134,22 @@ class Context:
         """Synchronise and raise on data-dependent device errors (key range / capacity)."""
         self._ok(lib.apc_check(self.h, _stream()))
 
+    def profile(self, on: bool):
+        """Bracket every eagerly launched kernel with CUDA events (see apc_profile_enable)."""
+        self._ok(lib.apc_profile_enable(self.h, int(bool(on))))
+
+    def profile_report(self) -> dict:
+        """``{kernel: (total_ms, launches)}`` since the last report; synchronises the device."""
+        buf = C.create_string_buffer(16384)
+        n = lib.apc_profile_report(self.h, buf, len(buf))
+        if n < 0:
+            self._ok(n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
+
     def _empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 

@@ -1,0 +1,191 @@
+"""Streaming / batched replay engine: the public per-GPU API for processing many scans.
+
+``ScanPipeline`` owns ``lanes`` independent lanes (CUDA stream + apc context + static device
+buffers + one captured CUDA graph of the whole preprocess() chain).  Frames are dealt to the
+lanes round-robin so that the copy engines and the SMs of one B200 stay busy: while one
+lane's kernels run, another lane's H2D / D2H copies and small latency-bound kernels overlap.
+
+Scans are independent units (the reference keeps no cross-frame state besides the cached
+static TF, pp.py:706), so multi-GPU is frame-parallel with no collective on the per-scan
+path; ``shard_frames`` deals contiguous blocks of frames to ranks and ``gather_outputs``
+all-gathers the per-GPU results (NCCL over NVLink on the GPU box, gloo in the CPU tests) for
+the batched PCAP-replay configuration only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _capi, engine
+
+
+def shard_frames(n_frames: int, world_size: int, rank: int) -> range:
+    """Contiguous block of frame indices owned by ``rank``."""
+    base, rem = divmod(n_frames, world_size)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def gather_outputs(send: torch.Tensor, counts: torch.Tensor, group=None):
+    """All-gather per-rank outputs.
+
+    ``send``   [F, pad_rows, 4] float32 - each frame's surviving points, zero padded;
+    ``counts`` [F] int32 - valid rows per frame.
+    Returns ``(recv [G, F, pad_rows, 4], all_counts [G, F])``.  Works on CUDA tensors with
+    the NCCL backend and on CPU tensors with gloo.
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    all_counts = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+    if send.is_cuda:
+        dist.all_gather_into_tensor(all_counts, counts.contiguous(), group=group)
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    else:
+        dist.all_gather(list(all_counts.unbind(0)), counts.contiguous(), group=group)
+        dist.all_gather(list(recv.unbind(0)), send.contiguous(), group=group)
+    return recv, all_counts
+
+
+class _Lane:
+    __slots__ = ("stream", "ctx", "d_in", "d_out", "d_counts", "d_plane", "h_counts", "h_out", "graph",
+                 "resident_graphs", "pending", "event", "desc")
+
+
+class ScanPipeline:
+    """preprocess() for a stream of same-layout scans on one GPU.
+
+    Parameters mirror the node's (``pointcloud_preprocessor.PointcloudPreprocessorNode``):
+    ``fields`` / ``point_step`` / ``n_points`` describe the PointCloud2 layout, ``filter_kw``
+    is passed to :func:`engine.make_filter_cfg`, ``stages`` to :func:`engine.make_pipeline_cfg`.
+    """
+
+    def __init__(self, fields, point_step: int, n_points: int, filter_kw: dict, stages: dict,
+                 lanes: int = 4, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA device required: this package has no CPU path")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        self.fields, self.point_step, self.n_points = list(fields), int(point_step), int(n_points)
+        self.frame_bytes = self.point_step * self.n_points
+        self.pcfg = engine.make_pipeline_cfg(engine.make_filter_cfg(**filter_kw), **stages)
+        self.lanes = []
+        for _ in range(lanes):
+            ln = _Lane()
+            ln.stream = torch.cuda.Stream(device=self.device)
+            ln.ctx = engine.Context(max_points=self.n_points, device=self.device_index)
+            ln.d_in = torch.zeros(self.frame_bytes, dtype=torch.uint8, device=self.device)
+            ln.d_out = torch.zeros((self.n_points, 4), dtype=torch.float32, device=self.device)
+            ln.d_counts = torch.zeros(8, dtype=torch.int32, device=self.device)
+            ln.d_plane = torch.zeros(8, dtype=torch.float64, device=self.device)
+            ln.h_counts = torch.zeros(8, dtype=torch.int32).pin_memory()
+            ln.h_out = torch.zeros((self.n_points, 4), dtype=torch.float32).pin_memory()
+            ln.desc = engine.make_cloud_desc(self.fields, self.point_step, self.n_points, ln.d_in)
+            ln.graph = ln.ctx.capture_pipeline([ln.desc], self.pcfg, ln.d_out, ln.d_counts, ln.d_plane)
+            ln.resident_graphs = {}
+            ln.pending = None
+            ln.event = torch.cuda.Event()
+            self.lanes.append(ln)
+        torch.cuda.synchronize(self.device)
+        #: kernels launched per scan by one graph replay (our own kernels; counted at capture)
+        self.kernels_per_scan = self._count_kernels()
+
+    def _count_kernels(self) -> int:
+        n = _capi.lib.apc_graph_kernel_count(self.lanes[0].graph)
+        if n < 0:
+            raise RuntimeError("apc_graph_kernel_count failed")
+        return n
+
+    def stage_profile(self) -> dict:
+        """One eager (non-graph) run on lane 0 with every kernel bracketed by CUDA events:
+        ``{kernel: (ms, launches)}`` for the frame currently in the lane's input buffer."""
+        ln = self.lanes[0]
+        with torch.cuda.stream(ln.stream):
+            ln.ctx.profile(True)
+            ln.ctx.pipeline_run([ln.desc], self.pcfg, ln.d_out, ln.d_counts, ln.d_plane)
+            rep = ln.ctx.profile_report()
+            ln.ctx.profile(False)
+        return rep
+
+    def close(self):
+        for ln in self.lanes:
+            ln.ctx.close()
+        self.lanes = []
+
+    # ---- end to end: host bytes in, host points out ----------------------------------------------
+    def process_host(self, frames, keep_outputs: bool = True):
+        """``frames``: pinned uint8 host tensors (one PointCloud2 ``data`` buffer each).
+        Returns ``(outputs, counts)``: per frame a float32 [n_out, 4] numpy array (x, y, z,
+        intensity) and the 8 pipeline counters.  H2D, kernels and D2H of different frames
+        overlap across lanes."""
+        results = [None] * len(frames)
+        counts = np.zeros((len(frames), 8), dtype=np.int32)
+        d2h_bytes = 0
+        S = len(self.lanes)
+        pend = [None] * S
+        for f, h_in in enumerate(frames):
+            ln = self.lanes[f % S]
+            if pend[f % S] is not None:
+                d2h_bytes += self._drain(ln, pend[f % S], results, counts, keep_outputs)
+            with torch.cuda.stream(ln.stream):
+                ln.d_in.copy_(h_in, non_blocking=True)
+                ln.ctx.launch_graph(ln.graph)
+                ln.h_counts.copy_(ln.d_counts, non_blocking=True)
+                ln.event.record(ln.stream)
+            pend[f % S] = f
+        for l, ln in enumerate(self.lanes):
+            if pend[l] is not None:
+                d2h_bytes += self._drain(ln, pend[l], results, counts, keep_outputs)
+        return results, counts, d2h_bytes
+
+    def _drain(self, ln, f, results, counts, keep_outputs):
+        ln.event.synchronize()
+        counts[f] = ln.h_counts.numpy()
+        if counts[f, _capi.CNT_STATUS] != 0:
+            ln.ctx.check()
+        n = int(counts[f, _capi.CNT_OUTPUT])
+        with torch.cuda.stream(ln.stream):
+            ln.h_out[:n].copy_(ln.d_out[:n], non_blocking=True)
+            ln.event.record(ln.stream)
+        ln.event.synchronize()
+        if keep_outputs:
+            results[f] = ln.h_out[:n].numpy().copy()
+        return n * 16 + 32
+
+    # ---- device resident: inputs already in HBM -----------------------------------------------------
+    def prepare_resident(self, pool: torch.Tensor, arena: torch.Tensor | None = None,
+                         counts_arena: torch.Tensor | None = None):
+        """Capture one graph per pool frame (``pool`` [F, frame_bytes] uint8 on the device) so
+        replaying reads each frame in place.  With ``arena`` [F, n_points, 4] / ``counts_arena``
+        [F, 8] every frame writes its own output slot (needed for the multi-GPU gather)."""
+        self._pool = pool
+        S = len(self.lanes)
+        for f in range(pool.shape[0]):
+            ln = self.lanes[f % S]
+            desc = engine.make_cloud_desc(self.fields, self.point_step, self.n_points, pool[f])
+            out = arena[f] if arena is not None else ln.d_out
+            cnt = counts_arena[f] if counts_arena is not None else ln.d_counts
+            ln.resident_graphs[f] = ln.ctx.capture_pipeline([desc], self.pcfg, out, cnt, ln.d_plane)
+        torch.cuda.synchronize(self.device)
+
+    def run_resident(self, frame_ids, main_stream=None):
+        """Replay the captured graphs for ``frame_ids`` across the lanes.  The caller's current
+        stream is the fork/join point, so CUDA events recorded on it bracket the whole batch."""
+        main = torch.cuda.current_stream(self.device) if main_stream is None else main_stream
+        S = len(self.lanes)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for ln in self.lanes:
+            ln.stream.wait_event(fork)
+        for f in frame_ids:
+            ln = self.lanes[f % S]
+            with torch.cuda.stream(ln.stream):
+                ln.ctx.launch_graph(ln.resident_graphs[f])
+        for ln in self.lanes:
+            ln.event.record(ln.stream)
+            main.wait_event(ln.event)
+
+    def check(self):
+        for ln in self.lanes:
+            ln.ctx.check()

@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the per-scan preprocessing hot path (BASELINE.json: Mpoints/s of the full
+preprocess pipeline; p50 per-scan latency @ 262k points).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): Ouster OS1-128 shape, 128 x 2048 = 262144-point
+synthetic spinning-LiDAR scans, full pipeline = read_points NaN skip + duplicate removal +
+non-finite filter + TF transform + ROI crop + 0.1 m voxel downsample + radius outlier
+removal (5 pts / 0.5 m) + RANSAC ground removal (0.2 m, n=5, 100 iterations, p=0.99).
+A "step" is one pass over a batch of FRAMES distinct scans (64 x 4.19 MB = 268 MB of input,
+larger than the 126 MB L2, so every step streams its input from HBM).  With N > 1 (torchrun)
+every rank processes its own FRAMES scans (frame-parallel, weak scaling) and the per-GPU
+outputs are all-gathered over NCCL once per step, overlapped with the next step's compute.
+
+One JSON line is printed by rank 0; see the keys at the bottom of ``main``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_BEAMS, N_AZ = 128, 2048
+N_POINTS = N_BEAMS * N_AZ
+LAYOUT = "xyzi16"
+POINT_STEP = 16
+TF = np.array([[0.9986295, -0.0523360, 0.0, 1.5], [0.0523360, 0.9986295, 0.0, -0.25],
+               [0.0, 0.0, 1.0, 0.2], [0.0, 0.0, 0.0, 1.0]])
+CROP = dict(min=[-60.0, -60.0, -20.0], max=[60.0, 60.0, 20.0], invert=False, mode=2)
+STAGES = dict(voxel_size=0.1, radius=dict(nb_points=5, radius=0.5),
+              ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=7))
+WORKLOAD = ("C2: Ouster OS1-128 shape 128x2048=262144 pts/scan, xyzi16 layout; NaN skip + dedup + non-finite + TF + "
+            "crop(+-60,+-60,+-20) + voxel 0.1 m + radius outliers(5, 0.5 m) + RANSAC ground(0.2, 5, 100, 0.99)")
+
+
+def make_frames(n_frames: int, seed0: int):
+    """``n_frames`` distinct scans: n/4 ray-cast scenes x 4 yaw-rotated copies (cheap variety)."""
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    n_base = max(1, (n_frames + 3) // 4)
+    msgs = []
+    for b in range(n_base):
+        scan = synth.lidar_scan(seed=seed0 + b, n_beams=N_BEAMS, n_az=N_AZ)
+        for r in range(4):
+            if len(msgs) == n_frames:
+                break
+            yaw = np.deg2rad(7.0 * r)
+            R = np.array([[np.cos(yaw), -np.sin(yaw), 0.0], [np.sin(yaw), np.cos(yaw), 0.0], [0.0, 0.0, 1.0]],
+                         dtype=np.float32)
+            sc = dict(scan)
+            sc["positions"] = (scan["positions"] @ R.T).astype(np.float32)
+            msgs.append(synth.pack_cloud(sc, LAYOUT))
+    return msgs
+
+
+def oracle_config():
+    from oracle import pipeline as opipe
+    cfg = opipe.default_config()
+    cfg.update(transforms=[TF], crop=CROP, voxel_size=STAGES["voxel_size"], radius=STAGES["radius"],
+               ground=STAGES["ground"])
+    return cfg
+
+
+def cpu_pipeline_seconds(msgs):
+    """The reference's CPU path (numpy verbatim expressions + Open3D semantics restated with
+    numpy / scipy cKDTree on all host cores) on the given scans."""
+    from oracle import pipeline as opipe
+    cfg = oracle_config()
+    t0 = time.perf_counter()
+    n_out = 0
+    for m in msgs:
+        n_out += opipe.preprocess(m, cfg)["positions"].shape[0]
+    return time.perf_counter() - t0, n_out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi SM clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(kernel: str, c) -> float | None:
+    """Algorithmic HBM bytes of one launch (DESIGN.md section 'Kernels'), from the measured
+    per-frame counts: N input, M filtered, V voxels, P after radius, ps = point_step."""
+    N, M, V = float(c["N"]), float(c["M"]), float(c["V"])
+    P = float(c["P_radius_in"])
+    table = {
+        "k_dedup_insert": N * POINT_STEP + 4 * N + 16 * N,          # read records, write p2slot, touch one 16 B slot
+        "k_frontend": N * POINT_STEP + 4 * N + 16 * M,              # read records + p2slot, write survivors
+        "k_voxel_insert": 16 * M + 4 * M + 48 * M,                  # read points, write p2slot, RMW one 48 B slot
+        "k_voxel_finalize": 4 * M + 4 * M + 48 * V + 16 * V,        # p2slot + first[], read/clean slots, write centroids
+        "k_grid_insert": 16 * P + 8 * P + 12 * P,                   # points, slot+rank, key/fill RMW
+        "k_grid_assign": 8 * P + 8 * P,
+        "k_grid_scatter": 16 * P + 12 * P + 16 * P,
+        "k_radius_query": 16 * P + 1 * P,                           # every neighbour read is an on-chip re-read
+        "k_grid_clean": 8 * P,
+        "k_select_by_mask": 16 * P + 1 * P + 16 * P,
+        "k_rs_score": 16 * float(c["P_ground_in"]),                 # one pass over the points for all hypotheses
+        "k_rs_final": 16 * float(c["P_ground_in"]) + float(c["P_ground_in"]),
+    }
+    return table.get(kernel)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: numpy
+    verbatim + Open3D restated; Open3D itself is not installable) on the host cores."""
+    if rank != 0:
+        return
+    import torch
+    frames_per_step = 2
+    msgs = make_frames(frames_per_step, seed0=0)
+    for _ in range(args.warmup):
+        cpu_pipeline_seconds(msgs[:1])
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_pipeline_seconds(msgs)
+        t += dt
+    ms = t / args.steps * 1e3
+    value = frames_per_step * N_POINTS / (ms * 1e-3) / 1e6
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "Mpoints/s full preprocess pipeline", "value": round(value, 4),
+        "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
+        "cpu_baseline": {"value": round(value, 4), "unit": "Mpoints/s", "cores": cores, "kind": "port",
+                         "sample": f"{frames_per_step} scans of the workload per step; numpy single-threaded + "
+                                   f"scipy cKDTree workers=-1 ({cores} cores, torch threads {torch.get_num_threads()})"},
+        "e2e": {"value": round(value, 4), "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="distinct scans per step per GPU")
+    ap.add_argument("--lanes", type=int, default=4, help="concurrent stream lanes per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from autodriver_pointcloud_preprocessor_b200 import _capi, replay
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = args.frames
+    msgs = make_frames(F, seed0=1000 * rank)
+    h_frames = [torch.frombuffer(bytearray(m.data), dtype=torch.uint8).pin_memory() for m in msgs]
+    pool = torch.stack([h.to(dev, non_blocking=True) for h in h_frames])
+    filter_kw = dict(skip_nans=True, dedup_mode=_capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True,
+                     transforms=[TF], crop=CROP)
+    pipe = replay.ScanPipeline(msgs[0].fields, POINT_STEP, N_POINTS, filter_kw, STAGES, lanes=args.lanes,
+                               device=local_rank)
+    arena = counts_arena = None
+    if world > 1:
+        arena = torch.zeros((F, N_POINTS, 4), dtype=torch.float32, device=dev)
+    counts_arena = torch.zeros((F, 8), dtype=torch.int32, device=dev)
+    pipe.prepare_resident(pool, arena, counts_arena)
+    frame_ids = list(range(F))
+    main_stream = torch.cuda.current_stream(dev)
+
+    # multi-GPU: all-gather the outputs of step k on a side stream while step k+1 computes
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    pad_rows, send = 0, None
+
+    def gather_step():
+        nonlocal send
+        done = torch.cuda.Event()
+        done.record(main_stream)
+        comm_stream.wait_event(done)
+        with torch.cuda.stream(comm_stream):
+            send.copy_(arena[:, :pad_rows])
+            replay.gather_outputs(send, counts_arena[:, _capi.CNT_OUTPUT].contiguous())
+
+    def step():
+        pipe.run_resident(frame_ids, main_stream)
+        if world > 1:
+            main_stream.wait_stream(comm_stream)      # previous gather has consumed the arena
+            gather_step()
+
+    # ---- warm-up (also sizes the gather slabs) -----------------------------------------------------
+    pipe.run_resident(frame_ids, main_stream)
+    torch.cuda.synchronize(dev)
+    pipe.check()
+    counts0 = counts_arena.cpu().numpy()
+    assert (counts0[:, _capi.CNT_STATUS] == 0).all()
+    if world > 1:
+        mx = torch.tensor([int(counts0[:, _capi.CNT_OUTPUT].max())], device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        pad_rows = min(N_POINTS, (int(mx.item()) * 9 // 8 + 1023) // 1024 * 1024)
+        send = torch.zeros((F, pad_rows, 4), dtype=torch.float32, device=dev)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: K steps, device events, barrier + synchronize on both sides ------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main_stream)
+    for _ in range(args.steps):
+        step()
+    if world > 1:
+        main_stream.wait_stream(comm_stream)
+    e1.record(main_stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * F * N_POINTS / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API: pinned host bytes in, host points out --------------------
+    pipe.process_host(h_frames[:8], keep_outputs=False)                      # warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        _, _, b = pipe.process_host(h_frames, keep_outputs=False)
+        d2h += b
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * F * N_POINTS / (e2e_ms * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 only: latency, per-kernel roofline, CPU baseline ---------------------------------------
+    ln = pipe.lanes[0]
+    lat = []
+    with torch.cuda.stream(ln.stream):
+        for rep in range(3):
+            for f in range(0, F, len(pipe.lanes)):                             # lane 0's own frames
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(ln.stream)
+                ln.ctx.launch_graph(ln.resident_graphs[f])
+                b.record(ln.stream)
+                b.synchronize()
+                lat.append(a.elapsed_time(b))
+    lat_e2e = []
+    for f in range(min(F, 32)):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        pipe.process_host([h_frames[f]], keep_outputs=True)
+        lat_e2e.append((time.perf_counter() - t0) * 1e3)
+
+    # per-kernel CUDA-event timings over several frames (eager launches on lane 0's stream)
+    prof = {}
+    n_prof = 8
+    for f in range(n_prof):
+        with torch.cuda.stream(ln.stream):
+            ln.d_in.copy_(pool[f], non_blocking=True)
+        for k, (ms, cnt) in pipe.stage_profile().items():
+            p = prof.setdefault(k, [0.0, 0])
+            p[0] += ms
+            p[1] += cnt
+    c = counts0.astype(np.float64).mean(axis=0)
+    cnt = {"N": c[_capi.CNT_INPUT], "M": c[_capi.CNT_FILTERED], "V": c[_capi.CNT_VOXELS],
+           "P_radius_in": c[_capi.CNT_VOXELS], "P_ground_in": c[_capi.CNT_AFTER_RADIUS], "out": c[_capi.CNT_OUTPUT]}
+    tot_ms = sum(v[0] for v in prof.values())
+    kernels = []
+    for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        per_launch_ms = ms / max(n, 1)
+        ab = algorithmic_bytes(k, cnt)
+        kernels.append({"kernel": k, "share": round(ms / tot_ms, 4), "us_per_launch": round(per_launch_ms * 1e3, 2),
+                        "algorithmic_MB": round(ab / 1e6, 3) if ab else None,
+                        "GBps": round(ab / (per_launch_ms * 1e-3) / 1e9, 1) if ab else None})
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = kernels[0]
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": round(dom["GBps"] / peak, 5) if dom["GBps"] else None, "traffic": None, "peak_source": peak_src,
+                "share_of_step": dom["share"], "us_per_launch": dom["us_per_launch"],
+                "note": "algorithmic bytes / CUDA-event duration of the dominant kernel, eager launch on its own "
+                        "stream, mean over 8 frames; per-kernel table under 'kernels'"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_cpu = 3
+        cpu_pipeline_seconds(msgs[:1])                                           # warm-up (thread pools, imports)
+        secs, _ = cpu_pipeline_seconds(msgs[:n_cpu])
+        cpu = {"value": round(n_cpu * N_POINTS / secs / 1e6, 4), "unit": "Mpoints/s", "cores": os.cpu_count(),
+               "kind": "port", "ms_per_scan": round(secs / n_cpu * 1e3, 1),
+               "sample": f"{n_cpu} scans of the same workload through oracle/pipeline.py (numpy + scipy cKDTree "
+                         f"workers=-1) after 1 warm-up scan"}
+
+    line = {
+        "metric": "Mpoints/s full preprocess pipeline", "value": round(value, 2), "unit": "Mpoints/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "lanes": args.lanes,
+                   "input_bytes_per_step_per_gpu": F * N_POINTS * POINT_STEP,
+                   "l2": "inputs larger than L2 (268 MB of distinct scans per step vs 126 MB L2)",
+                   "multi_gpu": "frame-parallel, no per-scan collective; per-step NCCL all-gather of outputs "
+                                "overlapped with the next step" if world > 1 else "single GPU"},
+        "p50_latency_ms": round(float(np.median(lat)), 4), "p99_latency_ms": round(float(np.percentile(lat, 99)), 4),
+        "p50_latency_e2e_ms": round(float(np.median(lat_e2e)), 4),
+        "points_per_scan": {k: round(float(v), 1) for k, v in cnt.items()},
+        "e2e": {"value": round(e2e_value, 2), "unit": "Mpoints/s", "h2d_bytes_per_step": F * N_POINTS * POINT_STEP,
+                "d2h_bytes_per_step": int(d2h / e2e_steps), "ms_per_step": round(e2e_ms, 3)},
+        "gpu_launches": int(pipe.kernels_per_scan * F * args.steps),
+        "kernels_per_scan": int(pipe.kernels_per_scan),
+        "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,15 @@ int apc_check(apc_ctx* ctx, void* stream);
 int apc_version(void);
 uint32_t apc_ctx_max_points(const apc_ctx* ctx);
 
+/* Per-kernel timing, the device-side counterpart of the reference's processing_times dict
+ * (pp.py:322, filled at pp.py:417-678).  While enabled, every kernel launched through this
+ * context is bracketed by CUDA events on its launching stream (eager calls only - not while
+ * capturing a graph).  apc_profile_report synchronises the device, writes one line
+ * "<kernel> <total_ms> <launches>\n" per kernel name into buf (NUL-terminated, truncated to
+ * buf_len), clears the collected samples and returns the number of bytes written. */
+int apc_profile_enable(apc_ctx* ctx, int on);
+int apc_profile_report(apc_ctx* ctx, char* buf, uint32_t buf_len);
+
 /* ---- (1)+(2)+(6) unpack, transform, filter, compact, concat --------------------- */
 
 /* Fused front end over 1..APC_MAX_CLOUDS PointCloud2 byte buffers, in one launch:
@@ -265,6 +274,8 @@ int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint3
                                uint32_t* out_counts_dev, double* out_plane_dev,
                                apc_graph** out_graph);
 int apc_graph_launch(apc_ctx* ctx, apc_graph* graph, void* stream);
+/* number of kernel nodes one replay of the graph launches (>= 0) or a negative apc_status */
+int apc_graph_kernel_count(const apc_graph* graph);
 int apc_graph_destroy(apc_graph* graph);
 
 #ifdef __cplusplus
