@@ -154,6 +154,10 @@ __device__ __forceinline__ float d2_f32(float ax, float ay, float az, float bx, 
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// 27 neighbour cells as dx+1 + 3*(dy+1) + 9*(dz+1), ordered centre, 6 faces, 12 edges, 8 corners
+__constant__ int8_t c_cell_order[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25,
+                                         0, 2, 6, 8, 18, 20, 24, 26};
+
 // ---- radius query -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
@@ -166,17 +170,19 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
     int32_t ix, iy, iz;
     grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
     uint32_t cnt = 0;
-    for (int dz = -1; dz <= 1 && (need_counts || cnt < nb_points); ++dz)
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
-          if (s == GRID_NOSLOT) continue;
-          const uint32_t b = g.start[s], e = b + g.fill[s];
-          for (uint32_t t = b; t < e; ++t) {
-            const float4 p = g.sorted[t];
-            cnt += (d2_f32(q.x, q.y, q.z, p.x, p.y, p.z) <= r2) ? 1u : 0u;
-          }
-        }
+    // own cell first, then faces, edges, corners: when only the keep/drop decision is wanted
+    // most points reach nb_points inside their own cell and stop there
+    for (int c27 = 0; c27 < 27 && (need_counts || cnt < nb_points); ++c27) {
+      const int code = c_cell_order[c27];
+      const int dx = code % 3 - 1, dy = (code / 3) % 3 - 1, dz = code / 9 - 1;
+      const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
+      if (s == GRID_NOSLOT) continue;
+      const uint32_t b = g.start[s], e = b + g.fill[s];
+      for (uint32_t t = b; t < e; ++t) {
+        const float4 p = g.sorted[t];
+        cnt += (d2_f32(q.x, q.y, q.z, p.x, p.y, p.z) <= r2) ? 1u : 0u;
+      }
+    }
     mask[orig] = cnt >= nb_points ? 1 : 0;
     if (counts) counts[orig] = cnt;
   }

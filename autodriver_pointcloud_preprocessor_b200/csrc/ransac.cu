@@ -140,7 +140,9 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
         const double d = plane_dist(s_pl[h], x, y, z);
         if (d < thr) {
           cnt[h] += 1u;
-          err[h] += __double2ull_rd(__dmul_rn(__dmul_rn(d, d), scale));
+          // d < thr => d^2 * 2^32/thr^2 < 2^32 (saturating at 2^32-1 in the 1-ulp corner):
+          // a single native F2I.U32.F64 instead of the emulated 64-bit conversion
+          err[h] += (unsigned long long)__double2uint_rd(__dmul_rn(__dmul_rn(d, d), scale));
         }
       }
     }
@@ -161,57 +163,90 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
 
 // Open3D's sequential selection + early-stop rule over the batched scores (one thread).
 // info = {best iteration | 0xffffffff, n_inliers (filled later), 0, 0}; plane8[4..7] = winner.
-__global__ void k_rs_select(const double* __restrict__ planes, const unsigned long long* __restrict__ scores,
-                            uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters, double prob,
-                            double* __restrict__ plane8, uint32_t* __restrict__ info) {
+#define RS_SELECT_CHUNK 512
+__global__ void __launch_bounds__(256)
+k_rs_select(const double* __restrict__ planes, const unsigned long long* __restrict__ scores,
+            uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters, double prob,
+            double* __restrict__ plane8, uint32_t* __restrict__ info) {
+  // the scan is inherently sequential, its loads are not: the CTA stages the scores (and a
+  // validity flag per hypothesis) in shared memory, then thread 0 walks them
+  __shared__ unsigned long long s_inl[RS_SELECT_CHUNK], s_err[RS_SELECT_CHUNK];
+  __shared__ uint8_t s_valid[RS_SELECT_CHUNK];
+  __shared__ unsigned long long sb_inl, sb_err;
+  __shared__ uint32_t sb_it;
+  __shared__ double sb_break;
   const uint32_t P = apc_count(n_dev, n_max);
-  unsigned long long best_inl = 0, best_err = 0;
-  uint32_t best_it = 0xffffffffu;
-  double break_it = (double)iters;
   const double log1mp = prob < 1.0 ? log(1.0 - prob) : -__longlong_as_double(0x7ff0000000000000ll);
-  for (uint32_t it = 0; it < iters; ++it) {
-    if ((double)it > break_it) continue;
-    const double* pl = planes + 4 * (size_t)it;
-    if (pl[0] == 0.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0) continue;
-    const unsigned long long inl = scores[2 * (size_t)it], err = scores[2 * (size_t)it + 1];
-    if (inl > best_inl || (inl == best_inl && inl > 0 && err < best_err)) {
-      best_inl = inl; best_err = err; best_it = it;
-      if (inl >= P) {
-        break_it = 0.0;
-      } else {
-        const double fitness = __ddiv_rn((double)inl, (double)P);
-        double fn = fitness;
-        for (uint32_t j = 1; j < ransac_n; ++j) fn = __dmul_rn(fn, fitness);
-        const double denom = log(__dsub_rn(1.0, fn));
-        const double cand = (denom == 0.0) ? __longlong_as_double(0x7ff0000000000000ll) : __ddiv_rn(log1mp, denom);
-        break_it = cand < (double)iters ? cand : (double)iters;
+  if (threadIdx.x == 0) { sb_inl = 0; sb_err = 0; sb_it = 0xffffffffu; sb_break = (double)iters; }
+  for (uint32_t c0 = 0; c0 < iters; c0 += RS_SELECT_CHUNK) {
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < RS_SELECT_CHUNK && c0 + t < iters; t += blockDim.x) {
+      const double* pl = planes + 4 * (size_t)(c0 + t);
+      s_valid[t] = !(pl[0] == 0.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0);
+      s_inl[t] = scores[2 * (size_t)(c0 + t)];
+      s_err[t] = scores[2 * (size_t)(c0 + t) + 1];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) continue;
+    unsigned long long best_inl = sb_inl, best_err = sb_err;
+    uint32_t best_it = sb_it;
+    double break_it = sb_break;
+    const uint32_t cend = min(iters, c0 + RS_SELECT_CHUNK);
+    for (uint32_t it = c0; it < cend; ++it) {
+      if ((double)it > break_it) continue;
+      if (!s_valid[it - c0]) continue;
+      const unsigned long long inl = s_inl[it - c0], err = s_err[it - c0];
+      if (inl > best_inl || (inl == best_inl && inl > 0 && err < best_err)) {
+        best_inl = inl; best_err = err; best_it = it;
+        if (inl >= P) {
+          break_it = 0.0;
+        } else {
+          const double fitness = __ddiv_rn((double)inl, (double)P);
+          double fn = fitness;
+          for (uint32_t j = 1; j < ransac_n; ++j) fn = __dmul_rn(fn, fitness);
+          const double denom = log(__dsub_rn(1.0, fn));
+          const double cand = (denom == 0.0) ? __longlong_as_double(0x7ff0000000000000ll) : __ddiv_rn(log1mp, denom);
+          break_it = cand < (double)iters ? cand : (double)iters;
+        }
       }
     }
+    sb_inl = best_inl; sb_err = best_err; sb_it = best_it; sb_break = break_it;
   }
-  info[0] = best_it; info[1] = 0; info[2] = 0; info[3] = 0;
-  for (int k = 0; k < 4; ++k) plane8[4 + k] = best_it == 0xffffffffu ? 0.0 : planes[4 * (size_t)best_it + k];
+  __syncthreads();
+  if (threadIdx.x == 0) { info[0] = sb_it; info[1] = 0; info[2] = 0; info[3] = 0; }
+  if (threadIdx.x < 4) plane8[4 + threadIdx.x] = sb_it == 0xffffffffu ? 0.0 : planes[4 * (size_t)sb_it + threadIdx.x];
 }
 
-// Final inliers against the winning hypothesis + per-CTA moment sums for the refit.
-__global__ void __launch_bounds__(256)
-k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const double* __restrict__ plane8,
-           const uint32_t* __restrict__ info, double thr, uint8_t* __restrict__ mask, double* __restrict__ partials) {
+#define CTR_RS_TICKET 20  // ctrl->counters slot: CTAs of k_rs_final that have published their partials
+
+// Final inliers against the winning hypothesis + moment sums for the least-squares refit.
+// Each CTA (1024 points) writes one partial; the last CTA to finish (ticket counter) sums the
+// partials in index order - a fixed reduction order, so the refit is deterministic - and
+// solves for the plane.
+__global__ void __launch_bounds__(APC_TILE_THREADS)
+k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, double* __restrict__ plane8,
+           uint32_t* __restrict__ info, double thr, uint8_t* __restrict__ mask, double* __restrict__ partials,
+           ApcCtrl* ctrl) {
   __shared__ double s_red[8][10];
+  __shared__ bool s_last;
   const uint32_t P = apc_count(n_dev, n_max);
   const bool have = info[0] != 0xffffffffu;
   const double pl[4] = {plane8[4], plane8[5], plane8[6], plane8[7]};
   double acc[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) {
-    const float4 p = pts[i];
-    const double x = p.x, y = p.y, z = p.z;
-    const bool inl = have && plane_dist(pl, x, y, z) < thr;
-    mask[i] = inl ? 1 : 0;
-    if (inl) {
-      acc[0] = 1.0; acc[1] = x; acc[2] = y; acc[3] = z;
-      acc[4] = x * x; acc[5] = x * y; acc[6] = x * z; acc[7] = y * y; acc[8] = y * z; acc[9] = z * z;
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = blockIdx.x * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    if (i < P) {
+      const float4 p = pts[i];
+      const double x = p.x, y = p.y, z = p.z;
+      const bool inl = have && plane_dist(pl, x, y, z) < thr;
+      mask[i] = inl ? 1 : 0;
+      if (inl) {
+        acc[0] += 1.0; acc[1] += x; acc[2] += y; acc[3] += z;
+        acc[4] += x * x; acc[5] += x * y; acc[6] += x * z; acc[7] += y * y; acc[8] += y * z; acc[9] += z * z;
+      }
     }
   }
 #pragma unroll
@@ -225,34 +260,36 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
     partials[(size_t)blockIdx.x * 10 + threadIdx.x] = s;
+    __threadfence();
   }
-}
-
-// One CTA sums the per-CTA partials in a fixed order, then refits the plane.
-__global__ void __launch_bounds__(256)
-k_rs_refit(const double* __restrict__ partials, uint32_t n_blocks_max, uint32_t n_max, const uint32_t* n_dev,
-           double* __restrict__ plane8, uint32_t* __restrict__ info) {
-  __shared__ double s_red[256][10];
-  const uint32_t P = apc_count(n_dev, n_max);
-  const uint32_t n_blocks = min(n_blocks_max, (P + 255u) / 256u);
-  double acc[10];
-  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-  for (uint32_t b = threadIdx.x; b < n_blocks; b += 256)
-    for (int k = 0; k < 10; ++k) acc[k] += partials[(size_t)b * 10 + k];
-  for (int k = 0; k < 10; ++k) s_red[threadIdx.x][k] = acc[k];
   __syncthreads();
-  for (int stride = 128; stride > 0; stride >>= 1) {
-    if (threadIdx.x < stride)
-      for (int k = 0; k < 10; ++k) s_red[threadIdx.x][k] += s_red[threadIdx.x + stride][k];
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->counters[CTR_RS_TICKET], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: stage 256 partial rows at a time in shared memory (parallel, coalesced loads),
+  // then thread k < 10 adds moment k in CTA order
+  __shared__ double s_part[256 * 10];
+  __shared__ double s_tot[10];
+  double run = 0.0;
+  const volatile double* vp = partials;
+  for (uint32_t b0 = 0; b0 < gridDim.x; b0 += 256) {
+    const uint32_t rows = min(256u, gridDim.x - b0);
     __syncthreads();
+    for (uint32_t e = threadIdx.x; e < rows * 10; e += blockDim.x) s_part[e] = vp[(size_t)b0 * 10 + e];
+    __syncthreads();
+    if (threadIdx.x < 10)
+      for (uint32_t b = 0; b < rows; ++b) run += s_part[b * 10 + threadIdx.x];
   }
+  if (threadIdx.x < 10) s_tot[threadIdx.x] = run;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const double n = s_red[0][0];
+    const double n = s_tot[0];
     info[1] = (uint32_t)n;
     if (n < 1.0) { plane8[0] = plane8[1] = plane8[2] = plane8[3] = 0.0; return; }
-    const double cx = s_red[0][1] / n, cy = s_red[0][2] / n, cz = s_red[0][3] / n;
-    const double xx = s_red[0][4] - n * cx * cx, xy = s_red[0][5] - n * cx * cy, xz = s_red[0][6] - n * cx * cz;
-    const double yy = s_red[0][7] - n * cy * cy, yz = s_red[0][8] - n * cy * cz, zz = s_red[0][9] - n * cz * cz;
+    const double cx = s_tot[1] / n, cy = s_tot[2] / n, cz = s_tot[3] / n;
+    const double xx = s_tot[4] - n * cx * cx, xy = s_tot[5] - n * cx * cy, xz = s_tot[6] - n * cx * cz;
+    const double yy = s_tot[7] - n * cy * cy, yz = s_tot[8] - n * cy * cz, zz = s_tot[9] - n * cz * cz;
     plane_from_moments(cx, cy, cz, xx, xy, xz, yy, yz, zz, plane8);
   }
 }
@@ -288,15 +325,11 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   }
   {
     APC_PROF(ctx, "k_rs_select", s);
-    k_rs_select<<<1, 1, 0, s>>>(ctx->rs_planes, ctx->rs_scores, n_max, n_dev, ransac_n, iters, prob, out_plane, out_info);
+    k_rs_select<<<1, 256, 0, s>>>(ctx->rs_planes, ctx->rs_scores, n_max, n_dev, ransac_n, iters, prob, out_plane, out_info);
   }
-  const uint32_t fb = apc_div_up(n_max, 256);
-  {
-    APC_PROF(ctx, "k_rs_final", s);
-    k_rs_final<<<fb, 256, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials);
-  }
-  APC_PROF(ctx, "k_rs_refit", s);
-  k_rs_refit<<<1, 256, 0, s>>>(ctx->rs_partials, fb, n_max, n_dev, out_plane, out_info);
+  APC_PROF(ctx, "k_rs_final", s);
+  k_rs_final<<<apc_div_up(n_max, APC_TILE_POINTS), APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr,
+                                                                             out_mask, ctx->rs_partials, ctx->ctrl);
   APC_LAUNCH_CHECK(ctx, "segment_plane");
   return APC_OK;
 }

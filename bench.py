@@ -90,23 +90,28 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        # one long-lived nvidia-smi in loop mode (20 ms period): many samples even in a short region
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+                    self.samples.append((time.perf_counter(), parts))
+        except Exception:
+            pass
 
-    def stop(self):
-        self._halt.set()
+    def stop(self, t_begin=0.0, t_end=float('inf')):
+        """Summary of the samples taken inside [t_begin, t_end] (perf_counter clock)."""
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=6)
+        inside = [p for (t, p) in self.samples if t_begin <= t <= t_end]
+        self.samples = inside if inside else [p for (_, p) in self.samples[-3:]]
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -170,7 +175,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="distinct scans per step per GPU")
@@ -230,6 +235,9 @@ def main():
             main_stream.wait_stream(comm_stream)      # previous gather has consumed the arena
             gather_step()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
     # ---- warm-up (also sizes the gather slabs) -----------------------------------------------------
     pipe.run_resident(frame_ids, main_stream)
     torch.cuda.synchronize(dev)
@@ -246,11 +254,10 @@ def main():
     torch.cuda.synchronize(dev)
 
     # ---- timed region: K steps, device events, barrier + synchronize on both sides ------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main_stream)
     for _ in range(args.steps):
@@ -262,7 +269,7 @@ def main():
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.perf_counter())
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -135,7 +135,7 @@ def score(P64: np.ndarray, plane: np.ndarray, thr: float):
     """``(inlier_count, err_q)`` with the integer error accumulator."""
     dist = plane_distance(P64, plane)
     inl = dist < np.float64(thr)
-    q = np.floor((dist[inl] * dist[inl]) * err_scale(thr)).astype(np.uint64)
+    q = np.minimum(np.floor((dist[inl] * dist[inl]) * err_scale(thr)), 4294967295.0).astype(np.uint64)
     return int(inl.sum()), int(q.sum(dtype=np.uint64))
 
 
