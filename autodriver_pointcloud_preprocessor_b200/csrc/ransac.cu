@@ -51,10 +51,12 @@ __device__ __forceinline__ void plane_from_moments(double cx, double cy, double 
 
 __global__ void k_rs_hypotheses(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n,
                                 uint32_t iters, uint64_t seed, const int32_t* __restrict__ table,
-                                double* __restrict__ planes) {
+                                double* __restrict__ planes, unsigned long long* __restrict__ scores) {
   const uint32_t P = apc_count(n_dev, n_max);
   const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= iters) return;
+  scores[2 * (size_t)it] = 0ull;       // tallies of the scoring pass start from zero
+  scores[2 * (size_t)it + 1] = 0ull;
   double* out = planes + 4 * (size_t)it;
   if (P < ransac_n) { out[0] = out[1] = out[2] = out[3] = 0.0; return; }
   uint32_t idx[RS_MAX_N];
@@ -101,20 +103,19 @@ __global__ void k_rs_hypotheses(const float4* __restrict__ pts, uint32_t n_max, 
   plane_from_moments(cx, cy, cz, xx, xy, xz, yy, yz, zz, out);
 }
 
-__global__ void k_rs_zero(unsigned long long* scores, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) scores[i] = 0ull;
-}
-
 __device__ __forceinline__ double plane_dist(const double* pl, double x, double y, double z) {
   return fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pl[0], x), __dmul_rn(pl[1], y)), __dmul_rn(pl[2], z)), pl[3]));
 }
 
-// grid = (point tiles, hypothesis chunks); scores[h] = {inlier count, sum floor(d^2 * scale)}
-__global__ void __launch_bounds__(APC_TILE_THREADS)
+// grid = (persistent CTAs striding over point tiles, hypothesis chunks);
+// scores[h] = {inlier count, sum floor(d^2 * scale)}.  Every CTA keeps its chunk of planes in
+// shared memory and its per-hypothesis tallies in registers across all the tiles it visits,
+// so the plane staging, the warp reduction and the atomics are paid once per CTA, not per tile.
+__global__ void __launch_bounds__(APC_TILE_THREADS, 2)
 k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const double* __restrict__ planes,
            uint32_t iters, double thr, double scale, unsigned long long* __restrict__ scores) {
   __shared__ double s_pl[RS_CHUNK][4];
+  __shared__ unsigned long long s_cnt[RS_CHUNK], s_err[RS_CHUNK];
   const uint32_t P = apc_count(n_dev, n_max);
   const uint32_t h0 = blockIdx.y * RS_CHUNK;
   const uint32_t nh = min((uint32_t)RS_CHUNK, iters - h0);
@@ -122,42 +123,53 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     const uint32_t h = threadIdx.x >> 2;
     s_pl[h][threadIdx.x & 3] = h < nh ? planes[4 * (size_t)(h0 + h) + (threadIdx.x & 3)] : 0.0;
   }
+  if (threadIdx.x < RS_CHUNK) { s_cnt[threadIdx.x] = 0; s_err[threadIdx.x] = 0; }
   __syncthreads();
-  const uint32_t first = blockIdx.x * APC_TILE_POINTS;
-  if (first >= P) return;
   uint32_t cnt[RS_CHUNK];
   unsigned long long err[RS_CHUNK];
 #pragma unroll
   for (int h = 0; h < RS_CHUNK; ++h) { cnt[h] = 0; err[h] = 0; }
+  for (uint32_t first = blockIdx.x * APC_TILE_POINTS; first < P; first += gridDim.x * APC_TILE_POINTS) {
+    float4 p[APC_TILE_ITEMS];
 #pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
-    const uint32_t i = first + j * APC_TILE_THREADS + threadIdx.x;
-    if (i < P) {
-      const float4 p = pts[i];
-      const double x = p.x, y = p.y, z = p.z;
+    for (int j = 0; j < APC_TILE_ITEMS; ++j) {   // all loads of the tile in flight before the math
+      const uint32_t i = first + j * APC_TILE_THREADS + threadIdx.x;
+      p[j] = i < P ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int h = 0; h < RS_CHUNK; ++h) {
-        const double d = plane_dist(s_pl[h], x, y, z);
-        if (d < thr) {
-          cnt[h] += 1u;
-          // d < thr => d^2 * 2^32/thr^2 < 2^32 (saturating at 2^32-1 in the 1-ulp corner):
-          // a single native F2I.U32.F64 instead of the emulated 64-bit conversion
-          err[h] += (unsigned long long)__double2uint_rd(__dmul_rn(__dmul_rn(d, d), scale));
+    for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+      const uint32_t i = first + j * APC_TILE_THREADS + threadIdx.x;
+      if (i < P) {
+        const double x = p[j].x, y = p[j].y, z = p[j].z;
+#pragma unroll
+        for (int h = 0; h < RS_CHUNK; ++h) {
+          const double d = plane_dist(s_pl[h], x, y, z);
+          if (d < thr) {
+            cnt[h] += 1u;
+            // d < thr => d^2 * 2^32/thr^2 < 2^32 (saturating at 2^32-1 in the 1-ulp corner):
+            // a single native F2I.U32.F64 instead of the emulated 64-bit conversion
+            err[h] += (unsigned long long)__double2uint_rd(__dmul_rn(__dmul_rn(d, d), scale));
+          }
         }
       }
     }
   }
+  // warp totals -> CTA totals in shared memory -> one pair of global atomics per hypothesis
 #pragma unroll
   for (int h = 0; h < RS_CHUNK; ++h) {
-    if ((uint32_t)h >= nh) break;
     const uint32_t c = __reduce_add_sync(0xffffffffu, cnt[h]);
     unsigned long long e = err[h];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane_id() == 0 && c) {
-      atomicAdd(&scores[2 * (size_t)(h0 + h)], (unsigned long long)c);
-      atomicAdd(&scores[2 * (size_t)(h0 + h) + 1], e);
+      atomicAdd(&s_cnt[h], (unsigned long long)c);
+      atomicAdd(&s_err[h], e);
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < nh && s_cnt[threadIdx.x]) {
+    atomicAdd(&scores[2 * (size_t)(h0 + threadIdx.x)], s_cnt[threadIdx.x]);
+    atomicAdd(&scores[2 * (size_t)(h0 + threadIdx.x) + 1], s_err[threadIdx.x]);
   }
 }
 
@@ -315,10 +327,13 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const double scale = 4294967296.0 / (thr * thr);
   {
     APC_PROF(ctx, "k_rs_hypotheses", s);
-    k_rs_hypotheses<<<apc_div_up(iters, 64), 64, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes);
-    k_rs_zero<<<apc_div_up(2 * iters, 256), 256, 0, s>>>(ctx->rs_scores, 2 * iters);
+    k_rs_hypotheses<<<apc_div_up(iters, 32), 32, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes,
+                                                         ctx->rs_scores);
   }
-  const dim3 grid(apc_div_up(n_max, APC_TILE_POINTS), apc_div_up(iters, RS_CHUNK));
+  // ~2 resident CTAs per SM in total (register-limited), each striding over point tiles
+  const uint32_t n_chunks = apc_div_up(iters, RS_CHUNK);
+  const uint32_t gx = min(apc_div_up(n_max, APC_TILE_POINTS), max(1u, (uint32_t)(APC_SM_COUNT * 2) / n_chunks));
+  const dim3 grid(gx, n_chunks);
   {
     APC_PROF(ctx, "k_rs_score", s);
     k_rs_score<<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ctx->rs_planes, iters, thr, scale, ctx->rs_scores);
