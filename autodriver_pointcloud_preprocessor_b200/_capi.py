@@ -78,6 +78,8 @@ def _load():
         "apc_duplicate_mask": [vp, vp, u32, vp, vp, vp],
         "apc_select_by_mask": [vp, vp, u32, vp, vp, i32, vp, vp, vp, vp],
         "apc_gather": [vp, vp, u32, vp, u32, vp, vp, vp],
+        "apc_pack_xyzi": [vp, vp, vp, u32, vp, vp],
+        "apc_split_xyzi": [vp, vp, u32, vp, vp, vp, vp],
         "apc_voxel_downsample": [vp, vp, u32, vp, C.c_float, vp, vp, vp, vp, vp],
         "apc_voxel_mean_attr": [vp, vp, vp, u32, vp, vp, vp, vp],
         "apc_radius_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp],
@@ -113,7 +115,8 @@ SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
            "apc_statistical_outliers", "apc_segment_plane", "apc_repack", "apc_pipeline_run",
            "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",
-           "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report"]
+           "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report", "apc_pack_xyzi",
+           "apc_split_xyzi"]
 
 
 class ApcError(RuntimeError):

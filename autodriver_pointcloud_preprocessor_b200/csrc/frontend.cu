@@ -581,3 +581,43 @@ extern "C" int apc_gather(apc_ctx* ctx, const void* src, uint32_t elem_size, con
   APC_LAUNCH_CHECK(ctx, "k_gather");
   return APC_OK;
 }
+
+// ---- carrier layout glue: positions float32[N,3] (+ intensity float32[N]) <-> SoA float4 -------
+// The Open3D-style carrier keeps `positions` as N x 3 (utils.py:102-104, pp.py:426) while every
+// kernel works on float4 records; these two kernels convert without touching the host.
+__global__ void k_pack_xyzi(const float* __restrict__ pos3, const float* __restrict__ inten, uint32_t n,
+                            float4* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = make_float4(pos3[3 * (size_t)i], pos3[3 * (size_t)i + 1], pos3[3 * (size_t)i + 2], inten ? inten[i] : 0.0f);
+}
+__global__ void k_split_xyzi(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev,
+                             float* __restrict__ pos3, float* __restrict__ inten) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = in[i];
+    pos3[3 * (size_t)i] = p.x; pos3[3 * (size_t)i + 1] = p.y; pos3[3 * (size_t)i + 2] = p.z;
+    if (inten) inten[i] = p.w;
+  }
+}
+
+extern "C" int apc_pack_xyzi(apc_ctx* ctx, const float* pos3, const float* intensity, uint32_t n, float* out_xyzi,
+                             void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  if (n == 0) return APC_OK;
+  APC_REQUIRE(ctx, pos3 && out_xyzi, "NULL pointer");
+  k_pack_xyzi<<<min(apc_div_up(n, 256), (uint32_t)APC_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
+      pos3, intensity, n, reinterpret_cast<float4*>(out_xyzi));
+  APC_LAUNCH_CHECK(ctx, "k_pack_xyzi");
+  return APC_OK;
+}
+
+extern "C" int apc_split_xyzi(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, float* out_pos3,
+                              float* out_intensity, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  if (n_max == 0) return APC_OK;
+  APC_REQUIRE(ctx, xyzi && out_pos3, "NULL pointer");
+  k_split_xyzi<<<min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(xyzi), n_max, n_dev, out_pos3, out_intensity);
+  APC_LAUNCH_CHECK(ctx, "k_split_xyzi");
+  return APC_OK;
+}

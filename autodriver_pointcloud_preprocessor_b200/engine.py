@@ -215,6 +215,21 @@ class Context:
         self._ok(lib.apc_gather(self.h, _ptr(src), elem, _ptr(idx), n, None, _ptr(out), _stream()))
         return out
 
+    def pack_xyzi(self, pos3, intensity=None):
+        """positions float32[N,3] (+ float32[N] intensity) -> SoA float4[N]."""
+        n = pos3.shape[0]
+        out = self._empty((max(n, 1), 4), torch.float32)
+        self._ok(lib.apc_pack_xyzi(self.h, _ptr(pos3), _ptr(intensity), n, _ptr(out), _stream()))
+        return out[:n]
+
+    def split_xyzi(self, xyzi, n=None, want_intensity=True):
+        """SoA float4 -> (positions float32[n,3], intensity float32[n] | None)."""
+        n = xyzi.shape[0] if n is None else int(n)
+        pos = self._empty((max(n, 1), 3), torch.float32)
+        inten = self._empty((max(n, 1),), torch.float32) if want_intensity else None
+        self._ok(lib.apc_split_xyzi(self.h, _ptr(xyzi), n, None, _ptr(pos), _ptr(inten), _stream()))
+        return pos[:n], (inten[:n] if inten is not None else None)
+
     # ---- voxel ---------------------------------------------------------------------------------
     def voxel_downsample(self, xyzi, voxel_size, want_p2v=False, want_counts=False, n_dev=None):
         n = xyzi.shape[0]

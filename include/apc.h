@@ -172,6 +172,14 @@ int apc_select_by_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
 int apc_gather(apc_ctx* ctx, const void* src, uint32_t elem_size, const uint32_t* idx,
                uint32_t n_max, const uint32_t* n_dev, void* out, void* stream);
 
+/* Carrier layout glue: the Open3D-style carrier keeps positions as float32[N,3] plus an
+ * optional float32[N] intensity (utils.py:102-104,121; pp.py:426); the kernels work on SoA
+ * float4.  Both directions stay on the device.  intensity / out_intensity may be NULL. */
+int apc_pack_xyzi(apc_ctx* ctx, const float* pos3, const float* intensity, uint32_t n,
+                  float* out_xyzi, void* stream);
+int apc_split_xyzi(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                   float* out_pos3, float* out_intensity, void* stream);
+
 /* ---- (3) voxel grid ---------------------------------------------------------------- */
 
 /* voxel_down_sample(voxel_size) (pp.py:509-512), mean reduction, float32 voxel index

@@ -1,0 +1,192 @@
+"""GPU tests of the drop-in layer: the Open3D-shaped carrier, the utils functions and the node
+callback (fused and staged paths) against the oracle and the reference-minted goldens."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+T_A = np.array([[0.9986295, -0.0523360, 0.0, 1.5], [0.0523360, 0.9986295, 0.0, -0.25], [0.0, 0.0, 1.0, 1.8],
+                [0.0, 0.0, 0.0, 1.0]])
+
+
+def scan_msg(layout="xyzirt22", seed=41, n_beams=32, n_az=512, **kw):
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    scan = synth.lidar_scan(seed=seed, n_beams=n_beams, n_az=n_az, **kw)
+    return scan, synth.pack_cloud(scan, layout, frame_id="lidar")
+
+
+def test_pointcloud_to_dict_matches_reference_conversion():
+    """utils.pointcloud_to_dict on the GPU == read_points + convert_pointcloud_to_numpy."""
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    from oracle import pc2
+    for layout in ("xyzi16", "xyzirt22", "ouster48"):
+        scan, msg = scan_msg(layout)
+        d, meta = utils.pointcloud_to_dict(msg, None, True, False, None)
+        ref, ref_meta = pc2.pointcloud_to_dict(msg, None, True, False, None)
+        assert {k: v for k, v in meta.items() if k != "header"} == {k: v for k, v in ref_meta.items() if k != "header"}
+        assert set(d) == set(ref)
+        for k in ref:
+            got = d[k].cpu().numpy()
+            assert got.dtype == ref[k].dtype, (layout, k)
+            assert np.array_equal(got, ref[k], equal_nan=True), (layout, k)
+
+
+def test_carrier_ops_against_oracle(golden_dir):
+    from autodriver_pointcloud_preprocessor_b200 import geometry as o3d
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    from oracle import dedup as odedup
+    from oracle import filters, voxel
+    scan, msg = scan_msg("xyzirt22", nan_frac=0.01)
+    d, meta = utils.pointcloud_to_dict(msg, None, False, False, None)       # keep NaNs: skip_nans False
+    for key in ("intensity", "ring", "time"):
+        d = utils.get_fields_from_dicts(key, d, meta)
+    pcd = utils.dict_to_open3d_tensor_pointcloud(d, device="CUDA:0")
+    pos = scan["positions"]
+    # duplicates -> non finite -> transform -> crop, like pp.py:450-506
+    p1, msg1 = utils.remove_duplicates(pcd, backend="open3d")
+    m_dup = odedup.open3d_mask(pos)
+    assert "remove_duplicated_points" in msg1 and len(p1.point.positions) == m_dup.sum()
+    p2, mask2 = p1.remove_non_finite_points(remove_nan=True, remove_infinite=True)
+    m_fin = filters.non_finite_mask(pos[m_dup])
+    assert np.array_equal(mask2.cpu().numpy(), m_fin)
+    keep = np.flatnonzero(m_dup)[m_fin]
+    p2.transform(o3d.Tensor(T_A, dtype=o3d.float32))
+    ref_pos = filters.transform(pos[keep], T_A)
+    assert np.array_equal(p2.point.positions.cpu().numpy().view(np.uint32), ref_pos.view(np.uint32))
+    for backend, mode in (("numpy", 0), ("torch", 1), ("open3d", 2)):
+        for invert in (False, True):
+            p3, cmsg = utils.crop_pointcloud(p2, backend=backend, min_bound=[-20.1, -33.3, -1.7],
+                                             max_bound=[27.3, 19.9, 2.9], invert=invert)
+            m = filters.crop_mask(ref_pos, [-20.1, -33.3, -1.7], [27.3, 19.9, 2.9], invert, mode)
+            assert len(p3.point.positions) == m.sum(), (backend, invert)
+            # every attribute travels with its point (select_by_mask gathers all of them)
+            assert np.array_equal(p3.point.ring.cpu().numpy().reshape(-1), scan["ring"][keep][m])
+            assert np.array_equal(p3.point.time.cpu().numpy().reshape(-1), scan["time"][keep][m].astype(np.float64))
+            if backend == "open3d":
+                assert "Using Open3D pointcloud.crop()" in cmsg
+    p3, _ = utils.crop_pointcloud(p2, backend="open3d", min_bound=[-60, -60, -20], max_bound=[60, 60, 20])
+    m = filters.crop_mask(ref_pos, [-60, -60, -20], [60, 60, 20])
+    # voxel grid: positions/intensity fixed-point mean, other attributes float32 mean then cast back
+    v = p3.voxel_down_sample(0.25)
+    ref = voxel.voxel_down_sample(ref_pos[m], 0.25, scan["intensity"][keep][m], fixed=True)
+    assert np.array_equal(v.point.positions.cpu().numpy().view(np.uint32), ref["positions"].view(np.uint32))
+    assert np.array_equal(v.point.intensity.cpu().numpy().reshape(-1).view(np.uint32), ref["intensity"].view(np.uint32))
+    ring_ref = voxel.centroids_o3d(scan["ring"][keep][m].astype(np.float32), ref["p2v"], ref["counts"].size)
+    got_ring = v.point.ring.cpu().numpy().reshape(-1)
+    assert got_ring.dtype == np.uint16
+    assert np.max(np.abs(got_ring.astype(np.float64) - ring_ref.astype(np.uint16))) <= 1      # float32 atomics order
+    # select_by_index(invert=True) == complement in order (pp.py:542)
+    idx = o3d.Tensor(torch.tensor([0, 5, 7], dtype=torch.int64))
+    rest = v.select_by_index(idx, invert=True)
+    assert len(rest.point.positions) == len(v.point.positions) - 3
+    assert np.array_equal(rest.point.positions.cpu().numpy()[:4], np.delete(ref["positions"], [0, 5, 7], axis=0)[:4])
+    # CPU-resident carrier: same results, tensors stay on the host
+    pc_cpu = p3.cpu()
+    v_cpu = pc_cpu.voxel_down_sample(0.25)
+    assert v_cpu.point.positions.is_cpu
+    assert np.array_equal(v_cpu.point.positions.numpy(), v.point.positions.cpu().numpy())
+
+
+def make_node(overrides, **kw):
+    from autodriver_pointcloud_preprocessor_b200.pointcloud_preprocessor import PointcloudPreprocessorNode
+    return PointcloudPreprocessorNode(parameter_overrides=overrides, **kw)
+
+
+def oracle_published(msg, cfg_update, T=None):
+    """What the reference would publish: oracle pipeline + prepare_pointcloud re-pack."""
+    from oracle import pc2
+    from oracle import pipeline as opipe
+    cfg = opipe.default_config()
+    cfg.update(cfg_update)
+    if T is not None:
+        cfg["transforms"] = [T]
+    return opipe.preprocess(msg, cfg), cfg
+
+
+def test_node_declares_reference_parameters(golden_dir):
+    import json
+    node = make_node({})
+    ref = json.load(open(os.path.join(golden_dir, "node_contract.json")))["parameters"]
+    for p in ref:
+        assert node.has_parameter(p["name"]), p["name"]
+        if p["name"] != "offset_pointcloud_matrix":
+            assert node.get_parameter(p["name"]).value == p["default"]
+    ns = make_node({}, parameter_namespace="front")
+    assert ns.has_parameter("front.voxel_size") and ns.parameter_namespace == "front."
+
+
+@pytest.mark.parametrize("layout,fused", [("xyzi16", "auto"), ("xyzirt22", "auto"), ("xyzirt22", "true"),
+                                          ("ouster48", "false")])
+def test_node_callback_end_to_end(layout, fused):
+    """callback(): bytes in -> published PointCloud2 bytes out, fused and staged paths."""
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    from oracle import pc2
+    scan, msg = scan_msg(layout, seed=43, n_beams=32, n_az=1024)
+    ground = dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=3)
+    node = make_node({"use_gpu": True, "voxel_size": 0.1, "remove_ground": True, "remove_ground.seed": 3,
+                      "remove_radius_outliers": True, "estimate_normals": False, "robot_frame": "base_link",
+                      "fused_pipeline": fused})
+    q = [0.0, 0.0, np.sin(0.02), np.cos(0.02)]
+    node.tf_buffer.set_transform("base_link", "lidar", (1.5, -0.25, 1.8), q)
+    node.callback(msg)
+    assert len(node.pointcloud_pub.messages) == 1, "callback dropped the frame"
+    out = node.pointcloud_pub.messages[0]
+    T = node.camera_to_robot_tf.cpu().numpy()
+    ref, cfg = oracle_published(msg, dict(voxel_size=0.1, ground=ground, radius=dict(nb_points=5, radius=0.5)), T)
+    assert out.width == ref["positions"].shape[0] and out.height == 1
+    assert out.header.frame_id == "base_link"                                   # pp.py:633-634
+    assert [f.name for f in out.fields] == [f.name for f in msg.fields]         # same names / types, re-packed
+    packed, step = pc2.packed_fields([f.name for f in msg.fields], [f.datatype for f in msg.fields])
+    assert out.point_step == step and [(f.name, f.offset, f.datatype) for f in out.fields] == packed
+    arr = np.frombuffer(out.data, dtype=pc2.dtype_from_fields(out.fields, out.point_step))
+    got = np.stack([arr["x"], arr["y"], arr["z"]], 1)
+    assert np.array_equal(got.view(np.uint32), ref["positions"].view(np.uint32))
+    assert np.array_equal(arr["intensity"].view(np.uint32), ref["intensity"].view(np.uint32))
+    uses_fused = fused == "true" or (fused == "auto" and layout == "xyzi16")
+    if "ring" in arr.dtype.names:
+        if uses_fused:
+            assert not arr["ring"].any()            # fused path carries xyz + intensity only (documented)
+        else:
+            assert arr["ring"].any()                # staged path carries / averages every known attribute
+    assert set(node.processing_times) >= {"ros_to_numpy", "preprocessing_time", "pointcloud_msg_parsing",
+                                          "pointcloud_pub", "total_callback_time", "tf_lookup"}
+    assert out.is_dense == (msg.is_dense and True)
+
+
+def test_node_dynamic_parameters():
+    from autodriver_pointcloud_preprocessor_b200._ros_compat import Parameter
+    node = make_node({"use_gpu": True, "estimate_normals": False})
+    ok = node.parameter_change_callback([Parameter("voxel_size", value=0.2)])
+    assert ok.successful and node.voxel_size == 0.2
+    assert not node.parameter_change_callback([Parameter("voxel_size", value="big")]).successful      # type guard
+    assert not node.parameter_change_callback([Parameter("no_such_parameter", value=1)]).successful   # pp.py:1001
+    assert not node.parameter_change_callback([Parameter("roi_min", value=[0.0, 1.0])]).successful    # length 3
+    assert node.parameter_change_callback([Parameter("roi_min", value=[-5.0, -5.0, -1.0])]).successful
+    assert node.roi_min == [-5.0, -5.0, -1.0]
+    # quirks kept from the reference: neither of these can be set through the callback
+    assert not node.parameter_change_callback([Parameter("offset_pointcloud_matrix", value=[1.0] * 16)]).successful
+    assert not node.parameter_change_callback([Parameter("pointcloud_save_ascii", value=True)]).successful
+    _, msg = scan_msg("xyzi16", seed=44)
+    node.callback(msg)
+    arr = node.pointcloud_pub.messages[-1]
+    assert arr.width > 0
+
+
+def test_concatenate_then_voxel():
+    """Config C3 in small through the host API: 4 sensors merged in one launch, then voxel."""
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    from autodriver_pointcloud_preprocessor_b200.pointcloud_concatenator import concatenate
+    from oracle import pipeline as opipe
+    from oracle import voxel
+    T = synth.sensor_extrinsics(4)
+    scans = [synth.lidar_scan(seed=60 + s, n_beams=16, n_az=512, nan_frac=0.0) for s in range(4)]
+    msgs = [synth.pack_cloud(sc, "xyzi16") for sc in scans]
+    xyzi, n, counts = concatenate(msgs, list(T), stages=dict(voxel_size=0.1))
+    merged = opipe.concat(scans, list(T))
+    ref = voxel.voxel_down_sample(merged["positions"], 0.1, merged["intensity"], fixed=True)
+    assert n == ref["positions"].shape[0]
+    assert np.array_equal(xyzi.cpu().numpy()[:, :3].view(np.uint32), ref["positions"].view(np.uint32))

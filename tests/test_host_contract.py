@@ -1,0 +1,165 @@
+"""Drop-in contract of the host-side mirror (CPU only): parameter table, method names, utils
+signatures and the pure-host helpers, all against fixtures minted from the reference
+(tests/golden/make_golden.py), plus the frame sharding / gather logic on gloo."""
+import inspect
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def contract(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "node_contract.json")))
+
+
+def test_parameter_table_matches_reference(contract):
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_preprocessor as pp
+    ref = contract["parameters"]
+    assert [p["name"] for p in ref] == [p[0] for p in pp.PARAMETERS]          # same names, same order
+    for r, (name, default, ptype) in zip(ref, pp.PARAMETERS):
+        if name == "offset_pointcloud_matrix":                                  # default is an expression: eye(4) flat
+            assert default == np.eye(4).flatten().tolist()
+        else:
+            assert default == r["default"], name
+            assert type(default) is type(r["default"]), name
+        want = None if r["type"] is None else getattr(pp.ParameterType, r["type"])
+        assert ptype == want, name
+    # additive parameters never shadow a reference name
+    assert not {p[0] for p in pp.EXTRA_PARAMETERS} & {p["name"] for p in ref}
+    assert sorted(pp.PROCESSING_TIME_KEYS) == contract["processing_times_keys"]
+
+
+def test_node_methods_match_reference(contract):
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_preprocessor as pp
+    cls = pp.PointcloudPreprocessorNode
+    for m in contract["methods"]:
+        assert hasattr(cls, m["name"]), m["name"]
+        if m["name"] == "__init__":
+            continue
+        got = list(inspect.signature(getattr(cls, m["name"])).parameters)
+        assert got[:len(m["args"])] == m["args"], m["name"]
+    init = inspect.signature(cls.__init__).parameters
+    assert list(init)[:4] == ["self", "node_name", "enabled", "parameter_namespace"]
+    assert init["node_name"].default == "pointcloud_preprocessor" and init["enabled"].default is True
+    assert callable(pp.main)
+
+
+def test_utils_signatures_match_reference(golden_dir):
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    sigs = json.load(open(os.path.join(golden_dir, "utils_signatures.json")))
+    for name, args in sigs.items():
+        fn = getattr(utils, name)
+        params = inspect.signature(fn).parameters
+        got = [p for p in params if not p.startswith("_")]
+        assert got == [a[0] for a in args], name
+        for (arg, default) in args:
+            if default is not None:
+                assert repr(params[arg].default) == default or str(params[arg].default) == default.strip("'\""), (name, arg)
+    for const in ("FIELD_DTYPE_MAP", "FIELD_DTYPE_MAP_INV", "VENDOR_MAPPINGS"):
+        assert hasattr(utils, const)
+
+
+def test_host_helpers_match_reference(golden_dir):
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    meta = json.load(open(os.path.join(golden_dir, "metadata.json")))
+    for entry in meta["mappings"]:
+        assert utils.get_pointcloud_metadata(entry["names"]) == entry["metadata"]
+    for entry in meta["packed"]:
+        fields, step = utils.numpy_struct_to_pointcloud2(entry["names"], entry["datatypes"])
+        assert step == entry["point_step"]
+        assert [[f.name, f.offset, f.datatype, f.count] for f in fields] == entry["fields"]
+    g = np.load(os.path.join(golden_dir, "rgb.npz"))
+    assert np.array_equal(utils.merge_rgb_fields(g["r"], g["g"], g["b"]).view(np.uint32), g["merged_float"].view(np.uint32))
+    assert np.array_equal(utils.merge_rgb_fields(g["r"], g["g"], g["b"], return_int=True), g["merged_int"])
+    assert np.array_equal(utils.extract_rgb_from_pointcloud(g["merged_float"]), g["extracted"])
+    assert np.array_equal(utils.rgb_int_to_float(g["colors"]).view(np.uint32), g["packed"].view(np.uint32))
+    assert np.array_equal(utils.rgb_to_intensity(g["colors"]), g["luminance"])
+    c = np.load(os.path.join(golden_dir, "convert.npz"))
+    for name in ("velodyne", "autoware", "livox", "f64xyz", "rgb"):
+        spec = meta[name]
+        dt = np.dtype({"names": [f[0] for f in spec["fields"]], "formats": [f[1] for f in spec["fields"]],
+                       "offsets": [f[2] for f in spec["fields"]], "itemsize": spec["itemsize"]})
+        arr = np.frombuffer(c[f"{name}__bytes"].tobytes(), dtype=dt)
+        d = utils.convert_pointcloud_to_numpy(arr, dict(spec["metadata"], field_names=dt.names))
+        for k, v in d.items():
+            assert np.array_equal(v, c[f"{name}__{k}"], equal_nan=True) and v.dtype == c[f"{name}__{k}"].dtype
+
+
+def test_dedup_backends_fail_loudly():
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    for backend in ("numpy", "torch"):
+        with pytest.raises(NotImplementedError):
+            utils.remove_duplicates(object(), backend=backend)
+
+
+def test_sensor_synchronizer():
+    from autodriver_pointcloud_preprocessor_b200.msgs import Header, PointCloud2, Time
+    from autodriver_pointcloud_preprocessor_b200.pointcloud_concatenator import SensorSynchronizer
+
+    def msg(t):
+        return PointCloud2(header=Header(stamp=Time(int(t), int((t % 1) * 1e9))))
+
+    s = SensorSynchronizer(3, mode="sync", slop=0.05)
+    assert s.add(0, msg(10.00)) is None and s.add(1, msg(10.01)) is None
+    ids, msgs = s.add(2, msg(10.02))
+    assert ids == [0, 1, 2] and len(msgs) == 3
+    assert s.add(0, msg(10.10)) is None and s.add(1, msg(10.11)) is None
+    assert s.add(2, msg(10.30)) is None                        # outside the slop: no set
+    r = SensorSynchronizer(3, mode="robust", slop=0.05, timeout=0.2)
+    assert r.add(0, msg(20.00)) is not None                    # only live sensor so far
+    assert r.add(0, msg(20.10)) is not None
+    r.add(1, msg(20.19))
+    out = r.add(0, msg(20.20))                                 # sensor 2 never reported: not waited for
+    assert out is not None and out[0] == [0, 1]
+
+
+def test_shard_frames_covers_everything():
+    from autodriver_pointcloud_preprocessor_b200.replay import shard_frames
+    for n, w in ((1024, 8), (1024, 3), (5, 8), (0, 2)):
+        got = [i for r in range(w) for i in shard_frames(n, w, r)]
+        assert got == list(range(n))
+        sizes = [len(shard_frames(n, w, r)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from autodriver_pointcloud_preprocessor_b200.replay import gather_outputs, shard_frames
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    frames = shard_frames(6, world, rank)
+    send = torch.zeros((len(frames), 4, 4))
+    counts = torch.zeros(len(frames), dtype=torch.int32)
+    for j, f in enumerate(frames):
+        counts[j] = f % 4 + 1
+        send[j, :counts[j]] = float(f)
+    recv, all_counts = gather_outputs(send, counts)
+    q.put((rank, recv.numpy(), all_counts.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gather_outputs_gloo_world2():
+    """The multi-GPU result exchange on CPU: 2 ranks, gloo, frame-parallel shards."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, recv, counts in results:
+        assert recv.shape == (2, 3, 4, 4) and counts.shape == (2, 3)
+        for g in range(2):
+            for j, f in enumerate(range(g * 3, g * 3 + 3)):
+                assert counts[g, j] == f % 4 + 1
+                assert (recv[g, j, :counts[g, j]] == f).all() and (recv[g, j, counts[g, j]:] == 0).all()
