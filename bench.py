@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="distinct scans per step per GPU")
-    ap.add_argument("--lanes", type=int, default=4, help="concurrent stream lanes per GPU")
+    ap.add_argument("--lanes", type=int, default=8, help="concurrent stream lanes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
