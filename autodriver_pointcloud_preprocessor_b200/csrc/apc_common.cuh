@@ -20,6 +20,18 @@ enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
 
 #define APC_NUM_SCAN_STATES 8
 
+// One voxel of the open-addressing table.  Everything a point touches when it is inserted
+// (key CAS, first-index min, count, four fixed-point sums) sits in one aligned 64-byte
+// half-line = two 32-byte L2 sectors, instead of five lines of five separate arrays.
+struct __align__(64) VoxSlot {
+  unsigned long long key;     // packed 63-bit voxel key, all ones = empty
+  uint32_t first;             // lowest point index in the voxel
+  uint32_t cnt;               // points in the voxel
+  unsigned long long acc[4];  // fixed-point sums: x, y, z (2^-24 m), intensity (2^-20)
+  unsigned long long pad[2];
+};
+static_assert(sizeof(VoxSlot) == 64, "VoxSlot must be one 64-byte half line");
+
 // Optional per-kernel timing with CUDA events on the launching stream (apc_profile_*).
 struct ApcProf {
   bool enabled = false;
@@ -38,10 +50,7 @@ struct apc_ctx {
   uint32_t max_tiles = 0;
   // hash tables (capacity = power of two >= 2*max_points)
   uint32_t hash_cap = 0;
-  uint64_t* vox_keys = nullptr;     // [hash_cap] packed voxel / cell keys
-  uint32_t* vox_first = nullptr;    // [hash_cap] lowest point index per slot
-  unsigned long long* vox_acc = nullptr;  // [hash_cap*4] fixed-point sums x,y,z,i
-  uint32_t* vox_cnt = nullptr;      // [hash_cap]
+  struct VoxSlot* vox_slots = nullptr;  // [hash_cap] 64-byte AoS slots {key, first, cnt, acc[4]}
   uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
   uint32_t* p2slot = nullptr;       // [max_points]
   uint4* dedup_slots = nullptr;     // [hash_cap] 128-bit {xbits,ybits,zbits,idx}

@@ -92,6 +92,61 @@ __device__ __forceinline__ uint32_t tile_ranks(const bool (&keep)[APC_TILE_ITEMS
 }
 static_assert(APC_TILE_ITEMS * (APC_TILE_THREADS / 32) == 32, "tile_ranks scans exactly 32 warp totals");
 
+// CTA-wide decoupled look-back: the whole CTA inspects a window of 256 predecessor tiles at
+// once (thread i looks at tile base-i), so a scan of <= 256 tiles - every per-scan launch at
+// 262k points - resolves in ONE round of independent loads instead of up to 8 dependent
+// 32-wide rounds by a single warp.  Called by all 256 threads; smem: uint32_t[34] (shared with
+// tile_ranks: slots 0..15 are reused here after the ranks have been read).
+__device__ __forceinline__ uint32_t scan_lookback_cta(uint64_t* __restrict__ state, uint32_t tile, uint32_t epoch,
+                                                      uint32_t aggregate, uint32_t* smem34) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t ep = epoch & 0x3fffffffu;
+  if (tile == 0) {
+    if (threadIdx.x == 0) st_volatile_u64(&state[0], scan_pack(ep, APC_ST_PREFIX, aggregate));
+    return 0;
+  }
+  if (threadIdx.x == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_AGGREGATE, aggregate));
+  __syncthreads();  // every thread has finished reading the rank scratch in smem34
+  uint32_t exclusive = 0;
+  int32_t base = (int32_t)tile - 1;
+  while (true) {
+    const int32_t idx = base - (int32_t)threadIdx.x;
+    uint32_t status, value;
+    do {
+      if (idx >= 0) {
+        const uint64_t w = ld_volatile_u64(&state[idx]);
+        status = ((uint32_t)(w >> 34) == ep) ? (uint32_t)((w >> 32) & 3u) : APC_ST_INVALID;
+        value = (uint32_t)w;
+      } else {
+        status = APC_ST_PREFIX;
+        value = 0;
+      }
+    } while (__any_sync(0xffffffffu, status == APC_ST_INVALID));
+    // per warp: sum of the values up to and including its nearest full prefix (or all 32)
+    const uint32_t pmask = __ballot_sync(0xffffffffu, status == APC_ST_PREFIX);
+    const uint32_t first = pmask ? (uint32_t)__ffs(pmask) - 1u : 31u;
+    const uint32_t wsum = warp_sum_u32(lane <= first ? value : 0u);
+    if (lane == 0) {
+      smem34[warp] = wsum;
+      smem34[8 + warp] = pmask ? 1u : 0u;
+    }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < APC_TILE_THREADS / 32; ++w) {  // warps in order of increasing distance
+      if (!found) {
+        exclusive += smem34[w];
+        found = smem34[8 + w] != 0u;
+      }
+    }
+    __syncthreads();
+    if (found) break;
+    base -= APC_TILE_THREADS;
+  }
+  if (threadIdx.x == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_PREFIX, exclusive + aggregate));
+  return exclusive;
+}
+
 // Full tile step: ranks + look-back.  Returns the global exclusive offset of this tile in
 // `tile_base` (all threads) and leaves per-item ranks in rank[].  smem: uint32_t[34].
 __device__ __forceinline__ uint32_t tile_compact_offsets(const bool (&keep)[APC_TILE_ITEMS],
@@ -100,13 +155,7 @@ __device__ __forceinline__ uint32_t tile_compact_offsets(const bool (&keep)[APC_
                                                          uint32_t tile, uint32_t epoch,
                                                          uint32_t* total_out, uint32_t n_tiles) {
   const uint32_t total = tile_ranks(keep, rank, smem34);
-  if ((threadIdx.x >> 5) == 0) {
-    const uint32_t excl = scan_lookback(state, tile, epoch, total);
-    if (lane_id() == 0) {
-      smem34[33] = excl;
-      if (tile == n_tiles - 1 && total_out) *total_out = excl + total;
-    }
-  }
-  __syncthreads();
-  return smem34[33];
+  const uint32_t excl = scan_lookback_cta(state, tile, epoch, total, smem34);
+  if (threadIdx.x == 0 && tile == n_tiles - 1 && total_out) *total_out = excl + total;
+  return excl;
 }

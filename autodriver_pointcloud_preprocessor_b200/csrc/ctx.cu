@@ -65,7 +65,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   apc_neighbors_release(ctx);
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
-  void* ptrs[] = {ctx->ctrl, ctx->vox_keys, ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank, ctx->p2slot,
+  void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
                   ctx->mask_a, ctx->idx_a, ctx->dev_counts};
@@ -101,10 +101,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   }
   A(dalloc(&ctx->ctrl, 1));
   for (auto& p : ctx->scan_state) A(dalloc(&p, ctx->max_tiles));
-  A(dalloc(&ctx->vox_keys, C));
-  A(dalloc(&ctx->vox_first, C));
-  A(dalloc(&ctx->vox_acc, C * 4));
-  A(dalloc(&ctx->vox_cnt, C));
+  A(dalloc(&ctx->vox_slots, C));
   A(dalloc(&ctx->vox_rank, C));
   A(dalloc(&ctx->p2slot, M));
   A(dalloc(&ctx->dedup_slots, C));

@@ -56,14 +56,21 @@ __device__ __forceinline__ uint4 atom_cas_b128(uint4* addr, uint4 cmp, uint4 val
 
 // Insert (xbits, ybits, zbits) -> keep the lowest point index per distinct bit pattern.
 // Slot layout {x, y, z, idx}; empty = all ones (idx 0xffffffff is never a point index).
-__device__ __forceinline__ void dedup_insert(uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl,
-                                             float x, float y, float z, uint32_t g) {
+__device__ __forceinline__ uint32_t dedup_home(float x, float y, float z, uint32_t mask) {
   const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
-  uint32_t slot = (uint32_t)mix64(((uint64_t)kx | ((uint64_t)ky << 32)) ^ mix64((uint64_t)kz + 0x9E3779B97F4A7C15ull)) & mask;
+  return (uint32_t)mix64(((uint64_t)kx | ((uint64_t)ky << 32)) ^ mix64((uint64_t)kz + 0x9E3779B97F4A7C15ull)) & mask;
+}
+__device__ __forceinline__ uint4 dedup_probe(uint4* slots, uint32_t slot, float x, float y, float z, uint32_t g) {
   const uint4 empty = make_uint4(DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY);
+  return atom_cas_b128(&slots[slot], empty, make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), g));
+}
+// Finishes an insert whose first probe at `slot` returned `old` (split from the probe so that a
+// thread can keep the first-probe round trips of several points in flight at once).
+__device__ __forceinline__ void dedup_resolve(uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl,
+                                              float x, float y, float z, uint32_t g, uint32_t slot, uint4 old) {
+  const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
   const uint4 mine = make_uint4(kx, ky, kz, g);
   for (uint32_t probe = 0; probe <= mask; ++probe) {
-    uint4 old = atom_cas_b128(&slots[slot], empty, mine);
     const bool was_empty = (old.x == DEDUP_EMPTY && old.y == DEDUP_EMPTY && old.z == DEDUP_EMPTY && old.w == DEDUP_EMPTY);
     if (was_empty) { p2slot[g] = slot; return; }
     if (old.x == kx && old.y == ky && old.z == kz) {
@@ -76,9 +83,15 @@ __device__ __forceinline__ void dedup_insert(uint4* slots, uint32_t mask, uint32
       return;
     }
     slot = (slot + 1) & mask;
+    old = dedup_probe(slots, slot, x, y, z, g);
   }
   atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
   p2slot[g] = 0;
+}
+__device__ __forceinline__ void dedup_insert(uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl,
+                                             float x, float y, float z, uint32_t g) {
+  const uint32_t slot = dedup_home(x, y, z, mask);
+  dedup_resolve(slots, mask, p2slot, ctrl, x, y, z, g, slot, dedup_probe(slots, slot, x, y, z, g));
 }
 
 // Pass 1 of duplicate removal over the raw byte buffers.
@@ -90,13 +103,21 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_
   const SegDev& s = prm.seg[si];
   TilePoint pt[APC_TILE_ITEMS];
   load_tile(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
+  uint32_t slot[APC_TILE_ITEMS];
+  uint4 old[APC_TILE_ITEMS];
+  const uint32_t g0 = s.point_begin + (tile - s.tile_begin) * APC_TILE_POINTS + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {  // the four first-probe CAS round trips overlap
     if (pt[j].valid && pt[j].no_nan) {
-      const uint32_t g = s.point_begin + (tile - s.tile_begin) * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
-      dedup_insert(prm.slots, prm.slot_mask, prm.p2slot, prm.ctrl, pt[j].x, pt[j].y, pt[j].z, g);
+      slot[j] = dedup_home(pt[j].x, pt[j].y, pt[j].z, prm.slot_mask);
+      old[j] = dedup_probe(prm.slots, slot[j], pt[j].x, pt[j].y, pt[j].z, g0 + j * APC_TILE_THREADS);
     }
   }
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j)
+    if (pt[j].valid && pt[j].no_nan)
+      dedup_resolve(prm.slots, prm.slot_mask, prm.p2slot, prm.ctrl, pt[j].x, pt[j].y, pt[j].z,
+                    g0 + j * APC_TILE_THREADS, slot[j], old[j]);
 }
 
 __device__ __forceinline__ bool crop_keep(const FrontendParams& prm, float x, float y, float z) {

@@ -107,13 +107,20 @@ __device__ __forceinline__ double plane_dist(const double* pl, double x, double 
   return fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pl[0], x), __dmul_rn(pl[1], y)), __dmul_rn(pl[2], z)), pl[3]));
 }
 
+#define RS_SELECT_CHUNK 512
+#define CTR_RS_SCORE_TICKET 21  // ctrl->counters slot: retired CTAs of k_rs_score
+__device__ void rs_select_cta(const double* __restrict__ planes, const unsigned long long* scores_in, uint32_t P,
+                              uint32_t ransac_n, uint32_t iters, double prob, double* __restrict__ plane8,
+                              uint32_t* __restrict__ info);
+
 // grid = (persistent CTAs striding over point tiles, hypothesis chunks);
 // scores[h] = {inlier count, sum floor(d^2 * scale)}.  Every CTA keeps its chunk of planes in
 // shared memory and its per-hypothesis tallies in registers across all the tiles it visits,
 // so the plane staging, the warp reduction and the atomics are paid once per CTA, not per tile.
 __global__ void __launch_bounds__(APC_TILE_THREADS, 2)
 k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const double* __restrict__ planes,
-           uint32_t iters, double thr, double scale, unsigned long long* __restrict__ scores) {
+           uint32_t iters, double thr, double scale, unsigned long long* scores, uint32_t ransac_n, double prob,
+           double* __restrict__ plane8, uint32_t* __restrict__ info, ApcCtrl* ctrl) {
   __shared__ double s_pl[RS_CHUNK][4];
   __shared__ unsigned long long s_cnt[RS_CHUNK], s_err[RS_CHUNK];
   const uint32_t P = apc_count(n_dev, n_max);
@@ -171,15 +178,24 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     atomicAdd(&scores[2 * (size_t)(h0 + threadIdx.x)], s_cnt[threadIdx.x]);
     atomicAdd(&scores[2 * (size_t)(h0 + threadIdx.x) + 1], s_err[threadIdx.x]);
   }
+  // the last CTA to retire (ticket) runs the sequential selection: one launch and one
+  // inter-kernel dependency less on the per-scan critical path
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->counters[CTR_RS_SCORE_TICKET], 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  rs_select_cta(planes, scores, P, ransac_n, iters, prob, plane8, info);
 }
 
-// Open3D's sequential selection + early-stop rule over the batched scores (one thread).
+// Open3D's sequential selection + early-stop rule over the batched scores, run by one CTA.
 // info = {best iteration | 0xffffffff, n_inliers (filled later), 0, 0}; plane8[4..7] = winner.
-#define RS_SELECT_CHUNK 512
-__global__ void __launch_bounds__(256)
-k_rs_select(const double* __restrict__ planes, const unsigned long long* __restrict__ scores,
-            uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters, double prob,
-            double* __restrict__ plane8, uint32_t* __restrict__ info) {
+__device__ void rs_select_cta(const double* __restrict__ planes, const unsigned long long* scores_in, uint32_t P,
+                              uint32_t ransac_n, uint32_t iters, double prob, double* __restrict__ plane8,
+                              uint32_t* __restrict__ info) {
+  const volatile unsigned long long* scores = scores_in;  // written by other CTAs' atomics: read through L2
   // the scan is inherently sequential, its loads are not: the CTA stages the scores (and a
   // validity flag per hypothesis) in shared memory, then thread 0 walks them
   __shared__ unsigned long long s_inl[RS_SELECT_CHUNK], s_err[RS_SELECT_CHUNK];
@@ -187,7 +203,6 @@ k_rs_select(const double* __restrict__ planes, const unsigned long long* __restr
   __shared__ unsigned long long sb_inl, sb_err;
   __shared__ uint32_t sb_it;
   __shared__ double sb_break;
-  const uint32_t P = apc_count(n_dev, n_max);
   const double log1mp = prob < 1.0 ? log(1.0 - prob) : -__longlong_as_double(0x7ff0000000000000ll);
   if (threadIdx.x == 0) { sb_inl = 0; sb_err = 0; sb_it = 0xffffffffu; sb_break = (double)iters; }
   for (uint32_t c0 = 0; c0 < iters; c0 += RS_SELECT_CHUNK) {
@@ -336,11 +351,8 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const dim3 grid(gx, n_chunks);
   {
     APC_PROF(ctx, "k_rs_score", s);
-    k_rs_score<<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ctx->rs_planes, iters, thr, scale, ctx->rs_scores);
-  }
-  {
-    APC_PROF(ctx, "k_rs_select", s);
-    k_rs_select<<<1, 256, 0, s>>>(ctx->rs_planes, ctx->rs_scores, n_max, n_dev, ransac_n, iters, prob, out_plane, out_info);
+    k_rs_score<<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ctx->rs_planes, iters, thr, scale, ctx->rs_scores,
+                                                 ransac_n, prob, out_plane, out_info, ctx->ctrl);
   }
   APC_PROF(ctx, "k_rs_final", s);
   k_rs_final<<<apc_div_up(n_max, APC_TILE_POINTS), APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr,

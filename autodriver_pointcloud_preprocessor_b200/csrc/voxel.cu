@@ -27,43 +27,64 @@ __device__ __forceinline__ bool voxel_key(float4 p, float vs, uint64_t& key) {
   return true;
 }
 
+#define VOX_ILP 4  // points per thread per round: their first-probe CAS round trips overlap
+
 __global__ void __launch_bounds__(256)
 k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
-               unsigned long long* __restrict__ keys, uint32_t* __restrict__ first,
-               unsigned long long* __restrict__ acc, uint32_t* __restrict__ cnt, uint32_t cap_mask,
-               uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
+               VoxSlot* __restrict__ slots, uint32_t cap_mask, uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = pts[i];
-    uint64_t key;
-    if (!voxel_key(p, vs, key)) {
-      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
-      p2slot[i] = VOX_NOSLOT;
-      continue;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * VOX_ILP) {
+    float4 p[VOX_ILP];
+    uint64_t key[VOX_ILP];
+    uint32_t slot[VOX_ILP];
+    unsigned long long old[VOX_ILP];
+    bool ok[VOX_ILP];
+#pragma unroll
+    for (int u = 0; u < VOX_ILP; ++u) {
+      const uint32_t i = i0 + u * stride;
+      ok[u] = i < n;
+      if (ok[u]) {
+        p[u] = pts[i];
+        ok[u] = voxel_key(p[u], vs, key[u]);
+        if (!ok[u]) {
+          atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+          p2slot[i] = VOX_NOSLOT;
+        }
+      }
+      slot[u] = ok[u] ? ((uint32_t)mix64(key[u]) & cap_mask) : 0u;
     }
-    uint32_t slot = (uint32_t)mix64(key) & cap_mask;
-    bool found = false;
-    for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
-      const unsigned long long old = atomicCAS(&keys[slot], VOX_EMPTY, (unsigned long long)key);
-      if (old == VOX_EMPTY || old == key) { found = true; break; }
-      slot = (slot + 1) & cap_mask;
+#pragma unroll
+    for (int u = 0; u < VOX_ILP; ++u)  // independent first probes, all in flight together
+      if (ok[u]) old[u] = atomicCAS(&slots[slot[u]].key, VOX_EMPTY, (unsigned long long)key[u]);
+#pragma unroll
+    for (int u = 0; u < VOX_ILP; ++u) {
+      if (!ok[u]) continue;
+      const uint32_t i = i0 + u * stride;
+      bool found = (old[u] == VOX_EMPTY || old[u] == key[u]);
+      for (uint32_t probe = 1; !found && probe <= cap_mask; ++probe) {  // rare: linear probing
+        slot[u] = (slot[u] + 1) & cap_mask;
+        const unsigned long long o = atomicCAS(&slots[slot[u]].key, VOX_EMPTY, (unsigned long long)key[u]);
+        found = (o == VOX_EMPTY || o == key[u]);
+      }
+      if (!found) {
+        atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+        p2slot[i] = VOX_NOSLOT;
+        continue;
+      }
+      VoxSlot* s = &slots[slot[u]];
+      p2slot[i] = slot[u];
+      atomicMin(&s->first, i);
+      atomicAdd(&s->cnt, 1u);
+      // rint(x * 2^24): exact product in float64, round-half-even like numpy.rint
+      atomicAdd(&s->acc[0], (unsigned long long)__double2ll_rn((double)p[u].x * 16777216.0));
+      atomicAdd(&s->acc[1], (unsigned long long)__double2ll_rn((double)p[u].y * 16777216.0));
+      atomicAdd(&s->acc[2], (unsigned long long)__double2ll_rn((double)p[u].z * 16777216.0));
+      long long qi = 0;
+      if (fabsf(p[u].w) < 1048576.0f) qi = __double2ll_rn((double)p[u].w * 1048576.0);
+      else atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+      atomicAdd(&s->acc[3], (unsigned long long)qi);
     }
-    if (!found) {
-      atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-      p2slot[i] = VOX_NOSLOT;
-      continue;
-    }
-    p2slot[i] = slot;
-    atomicMin(&first[slot], i);
-    atomicAdd(&cnt[slot], 1u);
-    // rint(x * 2^24): exact product in float64, round-half-even like numpy.rint
-    atomicAdd(&acc[4 * (size_t)slot + 0], (unsigned long long)__double2ll_rn((double)p.x * 16777216.0));
-    atomicAdd(&acc[4 * (size_t)slot + 1], (unsigned long long)__double2ll_rn((double)p.y * 16777216.0));
-    atomicAdd(&acc[4 * (size_t)slot + 2], (unsigned long long)__double2ll_rn((double)p.z * 16777216.0));
-    long long qi = 0;
-    if (fabsf(p.w) < 1048576.0f) qi = __double2ll_rn((double)p.w * 1048576.0);
-    else atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
-    atomicAdd(&acc[4 * (size_t)slot + 3], (unsigned long long)qi);
   }
 }
 
@@ -73,8 +94,7 @@ __device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, 
 
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
-                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ first,
-                 unsigned long long* __restrict__ acc, uint32_t* __restrict__ cnt, uint32_t* __restrict__ rank_of_slot,
+                 VoxSlot* __restrict__ slots, uint32_t* __restrict__ rank_of_slot,
                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
                  uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles) {
   __shared__ uint32_t sm_scan[34];
@@ -90,7 +110,7 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
     slot[j] = VOX_NOSLOT;
     if (i < n) {
       slot[j] = p2slot[i];
-      if (slot[j] != VOX_NOSLOT) is_first[j] = (first[slot[j]] == i);
+      if (slot[j] != VOX_NOSLOT) is_first[j] = (slots[slot[j]].first == i);
     }
   }
   uint32_t rank[APC_TILE_ITEMS];
@@ -100,20 +120,21 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
     if (is_first[j]) {
       const uint32_t s = slot[j];
       const uint32_t r = base + rank[j];
-      const uint32_t c = cnt[s];
+      // the slot is two 16-byte + one 32-byte aligned pieces of one 64-byte half line
+      uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
+      const uint4 head = raw[0];                                    // key lo/hi, first, cnt
+      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
+      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
+      const uint32_t c = head.w;
       const double dc = (double)c;
-      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&acc[4 * (size_t)s]);
-      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&acc[4 * (size_t)s + 2]);
       out[r] = make_float4(fixed_mean(a01.x, dc, 1.0 / 16777216.0), fixed_mean(a01.y, dc, 1.0 / 16777216.0),
                            fixed_mean(a23.x, dc, 1.0 / 16777216.0), fixed_mean(a23.y, dc, 1.0 / 1048576.0));
       if (out_counts) out_counts[r] = c;
       rank_of_slot[s] = r;
-      // self-clean the slot for the next frame
-      keys[s] = VOX_EMPTY;
-      first[s] = 0xffffffffu;
-      cnt[s] = 0u;
-      *reinterpret_cast<ulonglong2*>(&acc[4 * (size_t)s]) = make_ulonglong2(0ull, 0ull);
-      *reinterpret_cast<ulonglong2*>(&acc[4 * (size_t)s + 2]) = make_ulonglong2(0ull, 0ull);
+      // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0, acc = 0}
+      raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      raw[1] = make_uint4(0u, 0u, 0u, 0u);
+      raw[2] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -128,19 +149,18 @@ __global__ void k_voxel_p2v(uint32_t n_max, const uint32_t* n_dev, const uint32_
 }
 
 // Whole-table reset (context creation and error recovery only).
-__global__ void k_voxel_reset(unsigned long long* keys, uint32_t* first, unsigned long long* acc, uint32_t* cnt,
-                              uint32_t cap) {
+__global__ void k_voxel_reset(VoxSlot* slots, uint32_t cap) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
-    keys[s] = VOX_EMPTY;
-    first[s] = 0xffffffffu;
-    cnt[s] = 0u;
-    acc[4 * (size_t)s + 0] = 0; acc[4 * (size_t)s + 1] = 0; acc[4 * (size_t)s + 2] = 0; acc[4 * (size_t)s + 3] = 0;
+    uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
+    raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+    raw[1] = make_uint4(0u, 0u, 0u, 0u);
+    raw[2] = make_uint4(0u, 0u, 0u, 0u);
+    raw[3] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
 int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s) {
-  k_voxel_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
-                                                 ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap);
+  k_voxel_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(ctx->vox_slots, ctx->hash_cap);
   APC_LAUNCH_CHECK(ctx, "k_voxel_reset");
   return APC_OK;
 }
@@ -159,16 +179,14 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
   {
     APC_PROF(ctx, "k_voxel_insert", s);
-    k_voxel_insert<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size,
-                                          reinterpret_cast<unsigned long long*>(ctx->vox_keys), ctx->vox_first,
-                                          ctx->vox_acc, ctx->vox_cnt, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
+    const uint32_t ib = min(apc_div_up(n_max, 256 * VOX_ILP), (uint32_t)APC_SM_COUNT * 8);
+    k_voxel_insert<<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
+                                      ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
   }
   APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_PROF(ctx, "k_voxel_finalize", s);
-  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(n_max, n_dev, ctx->p2slot,
-                                                        reinterpret_cast<unsigned long long*>(ctx->vox_keys),
-                                                        ctx->vox_first, ctx->vox_acc, ctx->vox_cnt, ctx->vox_rank,
+  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
                                                         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts,
                                                         out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
   APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
