@@ -30,6 +30,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("APC_RS_TRACE"):   # phase timestamps inside k_rs_score (profiles/rs_trace.py)
+    NVCC_FLAGS.append("-DRS_TRACE")
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

@@ -64,7 +64,8 @@ struct apc_ctx {
   uint32_t* nb_count = nullptr;     // [max_points]
   // ransac
   double* rs_planes = nullptr;      // [max_iters*4]
-  unsigned long long* rs_scores = nullptr;  // [max_iters*2] {inliers, err}
+  unsigned long long* rs_scores = nullptr;  // per-CTA tally rows of k_rs_score {inliers, err}
+  unsigned long long* rs_scores_copy = nullptr;  // [max_iters*2] readable copy of the last call's tallies
   double* rs_partials = nullptr;    // refit partial sums
   uint32_t rs_max_iters = 0;
   // pipeline ping-pong buffers
@@ -147,6 +148,16 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// "Last CTA" ticket: called by ONE thread after a __syncthreads().  The acq_rel RMW at gpu scope
+// releases everything the CTA wrote before the barrier and acquires what the other CTAs released,
+// without the sequentially-consistent fence __threadfence() compiles to (MEMBAR.SC: measured
+// ~65 ns each and globally serialised, i.e. ~17 us across the 260 CTAs of one RANSAC launch).
+__device__ __forceinline__ uint32_t ticket_acq_rel(uint32_t* counter) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+  return old;
 }
 
 // streaming 128-bit load / store (inputs are read once, outputs written once)

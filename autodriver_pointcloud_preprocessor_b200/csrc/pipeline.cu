@@ -15,7 +15,7 @@ int apc_radius_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, d
 int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
-                              const int32_t*, double*, uint8_t*, uint32_t*, cudaStream_t);
+                              const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t);
 int apc_neighbors_prepare(apc_ctx*, int);
 
 // dev_counts layout inside the context
@@ -91,12 +91,11 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   if (has_ground) {
     float* out = dst();
     double* plane = out_plane_dev ? out_plane_dev : ctx->red_b;
+    // pp.py:542 select_by_index(inliers, invert=True) is fused into the final RANSAC pass: the
+    // non-ground points are written in order straight to `out`
     rc = apc_segment_plane_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->ground_distance_threshold, cfg->ground_ransac_n,
                                    cfg->ground_num_iterations, cfg->ground_probability, cfg->ground_seed, nullptr, plane,
-                                   ctx->mask_a, dc + DC_INFO, s);
-    if (rc) return rc;
-    // pp.py:542 select_by_index(inliers, invert=True): keep the non-ground points in order
-    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 1, out, nullptr, dc + DC_OUT, 4, s);
+                                   nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s);
     if (rc) return rc;
     cur = out;
     cur_cnt = DC_OUT;

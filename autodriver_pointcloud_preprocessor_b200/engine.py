@@ -281,6 +281,13 @@ class Context:
                                        _ptr(plane), _ptr(mask), _ptr(info), _stream()))
         return plane, mask[:n], info
 
+    def segment_plane_scores(self, num_iterations):
+        """``uint64[num_iterations, 2]`` = (inlier count, integer error sum) per hypothesis of the
+        most recent ``segment_plane`` / pipeline call (device tensor, viewed as int64)."""
+        out = torch.zeros((int(num_iterations), 2), dtype=torch.int64, device=self.device)
+        self._ok(lib.apc_segment_plane_scores(self.h, _ptr(out), int(num_iterations), _stream()))
+        return out
+
     # ---- repack --------------------------------------------------------------------------------------
     def repack(self, xyzi, out_fields, point_step, n_dev=None):
         """``out_fields``: list of ``(offset, datatype, source, attr_tensor | None)``."""

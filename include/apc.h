@@ -227,6 +227,13 @@ int apc_segment_plane(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
                       double* out_plane_dev, uint8_t* out_inlier_mask, uint32_t* out_info_dev,
                       void* stream);
 
+/* Per-hypothesis tallies of the most recent apc_segment_plane / pipeline call on this context:
+ * out_scores_dev uint64[2*num_iterations] = {inlier count, integer error sum} per iteration
+ * (the quantities Open3D's fitness / inlier_rmse are derived from, pp.py:535-540).  Diagnostic
+ * and test surface for the batched scoring kernel. */
+int apc_segment_plane_scores(apc_ctx* ctx, uint64_t* out_scores_dev, uint32_t num_iterations,
+                             void* stream);
+
 /* ---- (1 inverse) repack to PointCloud2 bytes ------------------------------------------ */
 
 typedef struct apc_out_field {

@@ -13,8 +13,9 @@ Definitions fixed here so the CUDA path can match bit for bit:
     accepted indices form the sample.  An explicit ``int32[iters, ransac_n]`` table may be
     supplied instead;
   * score: ``dist = |((a*x + b*y) + c*z) + d|``; inlier iff ``dist < thr`` (strict);
-    the error term is accumulated as an integer so it is independent of summation order:
-    ``err += floor(dist*dist * (2^32 / thr^2))`` over inliers;
+    the error term (a tie-breaker only) is accumulated as an integer so it is independent of
+    summation order: ``err += rint(d32*d32 * float32(2^16 / thr^2))`` over inliers, with
+    ``d32`` the distance evaluated with float32 fused multiply-adds (see ``score``);
   * selection has *sequential* semantics: iterations are visited in order; a hypothesis
     replaces the best when it has more inliers, or the same number and a smaller ``err``
     (equal inlier count => rmse order == err order); after each improvement
@@ -127,15 +128,51 @@ def plane_distance(P64: np.ndarray, plane: np.ndarray) -> np.ndarray:
     return np.abs(((a * P64[:, 0] + b * P64[:, 1]) + c * P64[:, 2]) + d)
 
 
-def err_scale(thr: float) -> np.float64:
-    return np.float64(4294967296.0) / (np.float64(thr) * np.float64(thr))
+ERR_BITS = 16   # error quantum = thr^2 / 2^16
+
+
+def err_scale(thr: float) -> np.float32:
+    """float32(2^16 / thr^2), the divide and the square in float64."""
+    return np.float32(np.float64(1 << ERR_BITS) / (np.float64(thr) * np.float64(thr)))
+
+
+def fma32(a, b, c) -> np.ndarray:
+    """Exact emulation of the float32 fused multiply-add ``round32(a*b + c)`` (one rounding).
+
+    ``a*b`` is exact in float64 (24+24 significand bits); the float64 sum ``s`` is rounded once,
+    and rounding ``s`` again to float32 can only go wrong when ``s`` lands exactly on a float32
+    midpoint while the true sum does not - detected with the TwoSum residual and nudged one
+    float64 ulp towards the true value first."""
+    p = np.asarray(a, dtype=np.float32).astype(np.float64) * np.asarray(b, dtype=np.float32).astype(np.float64)
+    c = np.broadcast_to(np.asarray(c, dtype=np.float32).astype(np.float64), p.shape)
+    s = p + c
+    bb = s - p
+    e = (p - (s - bb)) + (c - bb)                     # s + e == p + c exactly
+    mid = (s.view(np.uint64) & np.uint64((1 << 29) - 1)) == np.uint64(1 << 28)
+    fix = mid & (e != 0.0) & np.isfinite(s)
+    s = np.where(fix, np.nextafter(s, np.where(e > 0.0, np.inf, -np.inf)), s)
+    return s.astype(np.float32)
+
+
+def plane_distance_f32(P32: np.ndarray, plane: np.ndarray) -> np.ndarray:
+    """SIGNED float32 distance ``fma(c, z, fma(b, y, fma(a, x, d)))`` with the coefficients
+    rounded to float32 (the scoring kernel's FFMA2 chain)."""
+    a, b, c, d = (np.float32(v) for v in plane)
+    P32 = np.ascontiguousarray(P32, dtype=np.float32)
+    return fma32(c, P32[:, 2], fma32(b, P32[:, 1], fma32(a, P32[:, 0], d)))
 
 
 def score(P64: np.ndarray, plane: np.ndarray, thr: float):
-    """``(inlier_count, err_q)`` with the integer error accumulator."""
+    """``(inlier_count, err_q)``.  Inlier-ness is decided in float64 (``dist < thr``); the error
+    term - only a tie-breaker between hypotheses with equal inlier counts - is an integer sum
+    (independent of summation order) built from the float32 distance ``d32``:
+    ``q = rint(float32(d32*d32) * float32(2^16/thr^2))``, the product exact and the rounding
+    half-to-even (what ``fma(t, scale, 2^23)`` leaves in the float32 mantissa)."""
     dist = plane_distance(P64, plane)
     inl = dist < np.float64(thr)
-    q = np.minimum(np.floor((dist[inl] * dist[inl]) * err_scale(thr)), 4294967295.0).astype(np.uint64)
+    d32 = plane_distance_f32(P64[inl].astype(np.float32), plane)
+    t = (d32 * d32).astype(np.float32)
+    q = np.rint(t.astype(np.float64) * np.float64(err_scale(thr))).astype(np.uint64)
     return int(inl.sum()), int(q.sum(dtype=np.uint64))
 
 

@@ -313,6 +313,11 @@ def test_segment_plane_parity(env, ransac_n, iters):
     ctx.check()
     ref_plane, ref_inl, ri = ransac.segment_plane(host[:, :3], 0.2, ransac_n, iters, 0.99, seed=1234)
     info = info.cpu().numpy()
+    # every hypothesis' tallies: float64 inlier count and the integer error term, bit-exact
+    got_scores = ctx.segment_plane_scores(iters).cpu().numpy()
+    valid = np.any(ri["planes"] != 0.0, axis=1)
+    ref_scores = np.array([s if ok else (0, 0) for s, ok in zip(ri["scores"], valid)], dtype=np.int64)
+    assert np.array_equal(got_scores[valid], ref_scores[valid])
     assert int(info[0]) == ri["best_it"]                                    # same winning hypothesis
     p8 = plane8.cpu().numpy()
     assert np.array_equal(p8[4:], ri["best_plane"])                         # float64 hypothesis fit, bit-exact
