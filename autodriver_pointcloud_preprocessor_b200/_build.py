@@ -30,6 +30,8 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("APC_TRACE"):      # CTA timelines of the pipeline kernels (profiles/cta_trace.py)
+    NVCC_FLAGS.append("-DAPC_TRACE")
 if os.environ.get("APC_RS_TRACE"):   # phase timestamps inside k_rs_score (profiles/rs_trace.py)
     NVCC_FLAGS.append("-DRS_TRACE")
 

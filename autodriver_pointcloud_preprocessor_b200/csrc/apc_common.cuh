@@ -53,7 +53,7 @@ struct apc_ctx {
   struct VoxSlot* vox_slots = nullptr;  // [hash_cap] 64-byte AoS slots {key, first, cnt, acc[4]}
   uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
   uint32_t* p2slot = nullptr;       // [max_points]
-  uint4* dedup_slots = nullptr;     // [hash_cap] 128-bit {xbits,ybits,zbits,idx}
+  unsigned long long* dedup_slots = nullptr;  // [hash_cap] {key fingerprint:32 | lowest point index:32}
   // neighbour grid
   uint32_t* cell_start = nullptr;   // [hash_cap]
   uint32_t* cell_fill = nullptr;    // [hash_cap]
@@ -187,6 +187,31 @@ __device__ __forceinline__ void xform_f32(const float* __restrict__ T, float& x,
   y = __fdiv_rn(r1, w);
   z = __fdiv_rn(r2, w);
 }
+
+// ---- optional CTA timeline (build with APC_TRACE=1; read with profiles/cta_trace.py) ------------
+#ifdef APC_TRACE
+static __device__ unsigned long long g_apc_trace[8][2048][4];   // per translation unit: [kernel id][CTA][stamp]
+#define APC_TRACE_EXPORT(name)                                                              \
+  extern "C" int apc_debug_trace_##name(unsigned long long* out_host) {                     \
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, g_apc_trace, sizeof(g_apc_trace));       \
+    void* p = nullptr;                                                                      \
+    cudaGetSymbolAddress(&p, g_apc_trace);                                                  \
+    cudaMemset(p, 0, sizeof(g_apc_trace));                                                  \
+    return (int)e;                                                                          \
+  }
+__device__ __forceinline__ void apc_stamp(int kid, int k) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const uint32_t cta = blockIdx.x + blockIdx.y * gridDim.x;
+    if (cta < 2048) g_apc_trace[kid][cta][k] = t;
+  }
+}
+#define APC_STAMP(kid, k) apc_stamp(kid, k)
+#else
+#define APC_STAMP(kid, k) do { } while (0)
+#define APC_TRACE_EXPORT(name)
+#endif
 
 __device__ __forceinline__ bool is_nan_f(float v) { return v != v; }
 __device__ __forceinline__ bool is_inf_f(float v) { return fabsf(v) == __int_as_float(0x7f800000); }

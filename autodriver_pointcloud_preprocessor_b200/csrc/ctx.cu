@@ -7,6 +7,8 @@
 
 static thread_local std::string g_create_error;
 
+
+
 // table resets (context creation and error recovery); defined next to the kernels that own them
 int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s);
 int apc_dedup_reset(apc_ctx* ctx, cudaStream_t s);
@@ -88,7 +90,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   ctx->device = device;
   ctx->max_points = max_points;
   const size_t M = max_points;
-  ctx->hash_cap = next_pow2(2ull * M);
+  ctx->hash_cap = next_pow2(4ull * M);   // load factor <= 0.25: short probe chains (the warp-wide worst chain sets the latency)
   const size_t C = ctx->hash_cap;
   ctx->max_tiles = apc_div_up((uint32_t)(C > M ? C : M), 1024) + 8;
   ctx->rs_max_iters = 4096;

@@ -9,6 +9,7 @@
 // (crop_pointcloud), utils.py:271,297 + pp.py:542 (select_by_mask / select_by_index),
 // pointcloud_concatenator.py:1-5 (merge N sensors into one cloud in a target frame).
 #include "apc_load.cuh"
+APC_TRACE_EXPORT(frontend)
 
 struct FrontendParams {
   SegDev seg[APC_MAX_CLOUDS];
@@ -21,7 +22,7 @@ struct FrontendParams {
   double lo[3], hi[3];
   float lo32[3], hi32[3];
   // dedup table
-  uint4* slots;
+  unsigned long long* slots;
   uint32_t slot_mask;
   uint32_t* p2slot;
   // outputs
@@ -33,65 +34,107 @@ struct FrontendParams {
   ApcCtrl* ctrl;
 };
 
-// ---- 128-bit compare-and-swap (sm_90+) ----------------------------------------------------
-__device__ __forceinline__ uint4 atom_cas_b128(uint4* addr, uint4 cmp, uint4 val) {
-  uint64_t clo = (uint64_t)cmp.x | ((uint64_t)cmp.y << 32), chi = (uint64_t)cmp.z | ((uint64_t)cmp.w << 32);
-  uint64_t vlo = (uint64_t)val.x | ((uint64_t)val.y << 32), vhi = (uint64_t)val.z | ((uint64_t)val.w << 32);
-  uint64_t rlo, rhi;
-  asm volatile(
-      "{\n"
-      " .reg .b128 c, v, r;\n"
-      " mov.b128 c, {%2, %3};\n"
-      " mov.b128 v, {%4, %5};\n"
-      " atom.relaxed.gpu.global.cas.b128 r, [%6], c, v;\n"
-      " mov.b128 {%0, %1}, r;\n"
-      "}\n"
-      : "=l"(rlo), "=l"(rhi)
-      : "l"(clo), "l"(chi), "l"(vlo), "l"(vhi), "l"(addr)
-      : "memory");
-  return make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
+// ---- duplicate removal: 64-bit open-addressing slots {fingerprint:32 | lowest point index:32} -----
+// The 96-bit key (bit patterns of x, y, z) does not fit an atomic word, so a slot holds a 32-bit
+// fingerprint of the key next to the representative's index; a fingerprint hit is confirmed by
+// reading the representative's coordinates back from the input (only real duplicates and 2^-32
+// fingerprint collisions get there).  Equal keys then lower the index with atomicMin (same
+// fingerprint in the high half, so the minimum is the lower index).
+//
+// Probing is bucketised: a key's home is a 32-byte bucket of 4 slots (one L2 sector).  An insert
+// reads the whole bucket with one 2 x 128-bit load, picks the first slot that is empty or holds
+// its key, and issues ONE compare-and-swap - two dependent round trips whatever the probe length,
+// where slot-by-slot linear probing paid one atomic round trip per probe (profiled: the warp-wide
+// worst probe chain, not atomic throughput, was what made this kernel 38 us).  Slots of a bucket
+// fill strictly left to right and nothing is deleted while inserts run, so "first empty slot"
+// implies that every earlier insert of the same key is already visible to the scan.
+#define DEDUP_EMPTY 0xffffffffffffffffull
+#define DEDUP_BUCKET 4u
+
+__device__ __forceinline__ uint64_t dedup_hash(float x, float y, float z) {
+  const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
+  return mix64(((uint64_t)kx | ((uint64_t)ky << 32)) ^ mix64((uint64_t)kz + 0x9E3779B97F4A7C15ull));
+}
+__device__ __forceinline__ unsigned long long dedup_word(uint64_t h, uint32_t g) {
+  return ((unsigned long long)(h >> 32) << 32) | g;   // never all ones: g is a valid point index
 }
 
-#define DEDUP_EMPTY 0xffffffffu
-
-// Insert (xbits, ybits, zbits) -> keep the lowest point index per distinct bit pattern.
-// Slot layout {x, y, z, idx}; empty = all ones (idx 0xffffffff is never a point index).
-__device__ __forceinline__ uint32_t dedup_home(float x, float y, float z, uint32_t mask) {
-  const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
-  return (uint32_t)mix64(((uint64_t)kx | ((uint64_t)ky << 32)) ^ mix64((uint64_t)kz + 0x9E3779B97F4A7C15ull)) & mask;
-}
-__device__ __forceinline__ uint4 dedup_probe(uint4* slots, uint32_t slot, float x, float y, float z, uint32_t g) {
-  const uint4 empty = make_uint4(DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY);
-  return atom_cas_b128(&slots[slot], empty, make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), g));
-}
-// Finishes an insert whose first probe at `slot` returned `old` (split from the probe so that a
-// thread can keep the first-probe round trips of several points in flight at once).
-__device__ __forceinline__ void dedup_resolve(uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl,
-                                              float x, float y, float z, uint32_t g, uint32_t slot, uint4 old) {
-  const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
-  const uint4 mine = make_uint4(kx, ky, kz, g);
-  for (uint32_t probe = 0; probe <= mask; ++probe) {
-    const bool was_empty = (old.x == DEDUP_EMPTY && old.y == DEDUP_EMPTY && old.z == DEDUP_EMPTY && old.w == DEDUP_EMPTY);
-    if (was_empty) { p2slot[g] = slot; return; }
-    if (old.x == kx && old.y == ky && old.z == kz) {
-      while (old.w > g) {  // same key held by a later point: lower the representative index
-        const uint4 prev = atom_cas_b128(&slots[slot], old, mine);
-        if (prev.w == old.w) break;
-        old = prev;
+// Inserts ITEMS points per thread in lockstep: the bucket loads of all unfinished items are in
+// flight together, then their compare-and-swaps.  slot_mask = capacity - 1 (capacity a multiple of
+// the bucket size); `same(j, rep)` tells whether point `rep` has item j's x/y/z bit patterns.
+template <int ITEMS, typename SameFn>
+__device__ __forceinline__ void dedup_insert_items(unsigned long long* slots, uint32_t slot_mask, uint32_t* p2slot,
+                                                   ApcCtrl* ctrl, const uint64_t (&hash)[ITEMS],
+                                                   const unsigned long long (&word)[ITEMS], bool (&act)[ITEMS], SameFn same) {
+  uint32_t bucket[ITEMS], tries[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) { bucket[j] = (uint32_t)hash[j] & slot_mask & ~(DEDUP_BUCKET - 1u); tries[j] = 0; }
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) any |= act[j];
+  while (any) {
+    ulonglong2 lo[ITEMS], hi[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (act[j]) {   // L2 loads (.cg): a stale L1 line could hide a slot another SM has just filled
+        lo[j] = __ldcg(reinterpret_cast<const ulonglong2*>(slots + bucket[j]));
+        hi[j] = __ldcg(reinterpret_cast<const ulonglong2*>(slots + bucket[j]) + 1);
       }
-      p2slot[g] = slot;
-      return;
+    int want[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      want[j] = -1;
+      if (!act[j]) continue;
+      const unsigned long long v[4] = {lo[j].x, lo[j].y, hi[j].x, hi[j].y};
+      bool done = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (done || want[j] >= 0) continue;
+        if (v[k] == DEDUP_EMPTY) { want[j] = k; continue; }
+        if ((v[k] >> 32) == (word[j] >> 32) && same(j, (uint32_t)v[k])) {
+          if ((uint32_t)word[j] < (uint32_t)v[k]) atomicMin(&slots[bucket[j] + k], word[j]);   // lower the index
+          p2slot[(uint32_t)word[j]] = bucket[j] + k;
+          done = true;
+        }
+      }
+      if (done) { act[j] = false; continue; }
+      if (want[j] < 0) {   // bucket full of other keys: next bucket
+        bucket[j] = (bucket[j] + DEDUP_BUCKET) & slot_mask;
+        if (++tries[j] > (slot_mask >> 2)) {
+          atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+          p2slot[(uint32_t)word[j]] = 0;
+          act[j] = false;
+        }
+      }
     }
-    slot = (slot + 1) & mask;
-    old = dedup_probe(slots, slot, x, y, z, g);
+    unsigned long long old[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (act[j] && want[j] >= 0) old[j] = atomicCAS(&slots[bucket[j] + want[j]], DEDUP_EMPTY, word[j]);
+    any = false;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (act[j] && want[j] >= 0 && old[j] == DEDUP_EMPTY) {
+        p2slot[(uint32_t)word[j]] = bucket[j] + want[j];
+        act[j] = false;
+      }   // a lost race re-reads the same bucket on the next round
+      any |= act[j];
+    }
   }
-  atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-  p2slot[g] = 0;
 }
-__device__ __forceinline__ void dedup_insert(uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl,
-                                             float x, float y, float z, uint32_t g) {
-  const uint32_t slot = dedup_home(x, y, z, mask);
-  dedup_resolve(slots, mask, p2slot, ctrl, x, y, z, g, slot, dedup_probe(slots, slot, x, y, z, g));
+
+// x/y/z of point `g` of the launch, straight from the byte records (the confirm step above)
+template <typename P>
+__device__ __forceinline__ void load_xyz_global(const P& prm, uint32_t g, float& x, float& y, float& z) {
+  uint32_t si = 0;
+#pragma unroll
+  for (uint32_t k = 1; k < APC_MAX_CLOUDS; ++k)
+    if (k < prm.n_seg && g >= prm.seg[k].point_begin) si = k;
+  const SegDev& s = prm.seg[si];
+  const uint8_t* rec = s.data + (size_t)(g - s.point_begin) * s.step;
+  x = field_as_f32(rec + s.off[0], s.dt[0]);
+  y = field_as_f32(rec + s.off[1], s.dt[1]);
+  z = field_as_f32(rec + s.off[2], s.dt[2]);
 }
 
 // Pass 1 of duplicate removal over the raw byte buffers.
@@ -102,22 +145,28 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_
   const uint32_t si = find_segment(prm, tile);
   const SegDev& s = prm.seg[si];
   TilePoint pt[APC_TILE_ITEMS];
+  APC_STAMP(0, 0);
   load_tile(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
-  uint32_t slot[APC_TILE_ITEMS];
-  uint4 old[APC_TILE_ITEMS];
+  if (pt[0].x == 123456.f) APC_STAMP(0, 3);   // data dependence: the stamp below follows the loads
+  APC_STAMP(0, 1);
+  uint64_t hash[APC_TILE_ITEMS];
+  unsigned long long word[APC_TILE_ITEMS];
+  bool act[APC_TILE_ITEMS];
   const uint32_t g0 = s.point_begin + (tile - s.tile_begin) * APC_TILE_POINTS + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j) {  // the four first-probe CAS round trips overlap
-    if (pt[j].valid && pt[j].no_nan) {
-      slot[j] = dedup_home(pt[j].x, pt[j].y, pt[j].z, prm.slot_mask);
-      old[j] = dedup_probe(prm.slots, slot[j], pt[j].x, pt[j].y, pt[j].z, g0 + j * APC_TILE_THREADS);
-    }
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    act[j] = pt[j].valid && pt[j].no_nan;
+    hash[j] = dedup_hash(pt[j].x, pt[j].y, pt[j].z);
+    word[j] = dedup_word(hash[j], g0 + j * APC_TILE_THREADS);
   }
-#pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j)
-    if (pt[j].valid && pt[j].no_nan)
-      dedup_resolve(prm.slots, prm.slot_mask, prm.p2slot, prm.ctrl, pt[j].x, pt[j].y, pt[j].z,
-                    g0 + j * APC_TILE_THREADS, slot[j], old[j]);
+  dedup_insert_items<APC_TILE_ITEMS>(prm.slots, prm.slot_mask, prm.p2slot, prm.ctrl, hash, word, act,
+                                     [&](int j, uint32_t rep) {
+    float rx, ry, rz;
+    load_xyz_global(prm, rep, rx, ry, rz);
+    return __float_as_uint(rx) == __float_as_uint(pt[j].x) && __float_as_uint(ry) == __float_as_uint(pt[j].y) &&
+           __float_as_uint(rz) == __float_as_uint(pt[j].z);
+  });
+  APC_STAMP(0, 2);
 }
 
 __device__ __forceinline__ bool crop_keep(const FrontendParams& prm, float x, float y, float z) {
@@ -147,6 +196,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
   const SegDev& s = prm.seg[si];
   const uint32_t epoch = prm.ctrl->epoch;
   TilePoint pt[APC_TILE_ITEMS];
+  APC_STAMP(1, 0);
   load_tile(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
 
   bool keep[APC_TILE_ITEMS];
@@ -159,9 +209,9 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
     uint32_t st = alive ? APC_STAGE_NANSKIP : 0u;
     if (prm.dedup && alive) {
       const uint32_t sl = prm.p2slot[g];
-      alive = (prm.slots[sl].w == g);
+      alive = ((uint32_t)prm.slots[sl] == g);
       // the surviving representative resets its slot: the table is clean for the next frame
-      if (alive) prm.slots[sl] = make_uint4(DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY);
+      if (alive) prm.slots[sl] = DEDUP_EMPTY;
     }
     if (alive) st |= APC_STAGE_DEDUP;
     float x = pt[j].x, y = pt[j].y, z = pt[j].z;
@@ -177,8 +227,10 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
     if (prm.out_stage && pt[j].valid) prm.out_stage[g] = (uint8_t)st;
   }
   uint32_t rank[APC_TILE_ITEMS];
+  APC_STAMP(1, 1);
   const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, prm.scan_state, tile, epoch,
                                              prm.out_count, prm.n_tiles);
+  APC_STAMP(1, 2);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     if (keep[j]) {
@@ -187,6 +239,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
       if (prm.out_src) prm.out_src[o] = gidx[j];
     }
   }
+  APC_STAMP(1, 3);
 }
 
 // ---- generic fill (hash-table clears) -----------------------------------------------------
@@ -356,7 +409,7 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
 }
 
 int apc_dedup_reset(apc_ctx* ctx, cudaStream_t s) {
-  return apc_fill_u32(ctx, ctx->dedup_slots, DEDUP_EMPTY, (size_t)ctx->hash_cap * 4, s);
+  return apc_fill_u32(ctx, ctx->dedup_slots, 0xffffffffu, (size_t)ctx->hash_cap * 2, s);
 }
 
 extern "C" int apc_frontend(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
@@ -480,21 +533,28 @@ extern "C" int apc_non_finite_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_m
 }
 
 __global__ void k_dup_insert_soa(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev,
-                                 uint4* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl) {
+                                 unsigned long long* slots, uint32_t mask, uint32_t* p2slot, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = in[i];
-    dedup_insert(slots, mask, p2slot, ctrl, p.x, p.y, p.z, i);
+    const uint64_t hash[1] = {dedup_hash(p.x, p.y, p.z)};
+    const unsigned long long word[1] = {dedup_word(hash[0], i)};
+    bool act[1] = {true};
+    dedup_insert_items<1>(slots, mask, p2slot, ctrl, hash, word, act, [&](int, uint32_t rep) {
+      const float4 r = in[rep];
+      return __float_as_uint(r.x) == __float_as_uint(p.x) && __float_as_uint(r.y) == __float_as_uint(p.y) &&
+             __float_as_uint(r.z) == __float_as_uint(p.z);
+    });
   }
 }
-__global__ void k_dup_mask_soa(uint32_t n_max, const uint32_t* n_dev, uint4* __restrict__ slots,
+__global__ void k_dup_mask_soa(uint32_t n_max, const uint32_t* n_dev, unsigned long long* __restrict__ slots,
                                const uint32_t* __restrict__ p2slot, uint8_t* __restrict__ mask) {
   const uint32_t n = apc_count(n_dev, n_max);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t sl = p2slot[i];
-    const bool win = slots[sl].w == i;
+    const bool win = (uint32_t)slots[sl] == i;
     mask[i] = win ? 1 : 0;
-    if (win) slots[sl] = make_uint4(DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY, DEDUP_EMPTY);  // self-clean
+    if (win) slots[sl] = DEDUP_EMPTY;  // self-clean
   }
 }
 
@@ -525,6 +585,7 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
   const uint32_t tile = blockIdx.x;
   bool keep[APC_TILE_ITEMS];
   float4 v[APC_TILE_ITEMS];
+  APC_STAMP(2, 0);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
@@ -535,7 +596,9 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
     }
   }
   uint32_t rank[APC_TILE_ITEMS];
+  APC_STAMP(2, 1);
   const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+  APC_STAMP(2, 2);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     if (keep[j]) {
@@ -544,6 +607,7 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
       if (out_idx) out_idx[o] = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
     }
   }
+  APC_STAMP(2, 3);
 }
 
 int apc_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,

@@ -16,6 +16,7 @@
 // are (fewer than k points in range of the coarsest level) fall to an exact brute-force
 // kernel.  The table is cleaned by the points that own rank 0 of their cell, not by memset.
 #include "apc_scan.cuh"
+APC_TRACE_EXPORT(neighbors)
 
 #define GRID_EMPTY 0xffffffffffffffffull
 #define GRID_NOSLOT 0xffffffffu
@@ -50,13 +51,24 @@ __device__ __forceinline__ uint64_t grid_key(uint32_t level, int32_t ix, int32_t
   return ((uint64_t)level << 57) | ((uint64_t)(uint32_t)(ix + 262144) << 38) |
          ((uint64_t)(uint32_t)(iy + 262144) << 19) | (uint64_t)(uint32_t)(iz + 262144);
 }
+// Probing is bucketised like the duplicate table (frontend.cu): a key's home is a 32-byte bucket
+// of 4 key words read with one 2 x 128-bit load; buckets fill left to right and nothing is removed
+// while a grid is in use, so a lookup stops at the first empty word.
+#define GRID_BUCKET 4u
 __device__ __forceinline__ uint32_t grid_find(const GridDev& g, uint64_t key) {
-  uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
-  for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
-    const unsigned long long k = g.keys[s];
-    if (k == key) return s;
-    if (k == GRID_EMPTY) return GRID_NOSLOT;
-    s = (s + 1) & g.cap_mask;
+  uint32_t b = (uint32_t)mix64(key) & g.cap_mask & ~(GRID_BUCKET - 1u);
+  for (uint32_t tries = 0; tries <= (g.cap_mask >> 2); ++tries) {
+    const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(g.keys + b);
+    const ulonglong2 hi = *(reinterpret_cast<const ulonglong2*>(g.keys + b) + 1);
+    if (lo.x == key) return b;
+    if (lo.x == GRID_EMPTY) return GRID_NOSLOT;
+    if (lo.y == key) return b + 1;
+    if (lo.y == GRID_EMPTY) return GRID_NOSLOT;
+    if (hi.x == key) return b + 2;
+    if (hi.x == GRID_EMPTY) return GRID_NOSLOT;
+    if (hi.y == key) return b + 3;
+    if (hi.y == GRID_EMPTY) return GRID_NOSLOT;
+    b = (b + GRID_BUCKET) & g.cap_mask;
   }
   return GRID_NOSLOT;
 }
@@ -72,12 +84,21 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
     int32_t ix, iy, iz;
     uint32_t slot = GRID_NOSLOT, rank = 0;
     if (grid_coord(p.x, p.y, p.z, c, ix, iy, iz)) {
-      const uint64_t key = grid_key(level, ix, iy, iz);
-      uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
-      for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
-        const unsigned long long old = atomicCAS(&g.keys[s], GRID_EMPTY, (unsigned long long)key);
-        if (old == GRID_EMPTY || old == key) { slot = s; break; }
-        s = (s + 1) & g.cap_mask;
+      const unsigned long long key = grid_key(level, ix, iy, iz);
+      uint32_t b = (uint32_t)mix64(key) & g.cap_mask & ~(GRID_BUCKET - 1u);
+      for (uint32_t tries = 0; slot == GRID_NOSLOT && tries <= (g.cap_mask >> 2); ++tries) {
+        // one L2 read of the bucket (.cg: never a stale L1 copy), then at most one CAS per slot
+        const ulonglong2 lo = __ldcg(reinterpret_cast<const ulonglong2*>(g.keys + b));
+        const ulonglong2 hi = __ldcg(reinterpret_cast<const ulonglong2*>(g.keys + b) + 1);
+        const unsigned long long v[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (slot != GRID_NOSLOT) continue;
+          unsigned long long cur = v[k];
+          if (cur == GRID_EMPTY) cur = atomicCAS(&g.keys[b + k], GRID_EMPTY, key);   // the occupant if the race is lost
+          if (cur == GRID_EMPTY || cur == key) slot = b + k;
+        }
+        b = (b + GRID_BUCKET) & g.cap_mask;
       }
       if (slot == GRID_NOSLOT) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
       else rank = atomicAdd(&g.fill[slot], 1u);
@@ -164,6 +185,7 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
                uint8_t* __restrict__ mask, uint32_t* __restrict__ counts) {
   const uint32_t n = apc_count(n_dev, n_max);
   const float c = g.cell[0];
+  APC_STAMP(0, 0);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
@@ -186,6 +208,7 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
     mask[orig] = cnt >= nb_points ? 1 : 0;
     if (counts) counts[orig] = cnt;
   }
+  APC_STAMP(0, 1);
 }
 
 // ---- KNN query ---------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 // The table is self-cleaning: the thread that finalises a voxel resets its slot, so no
 // per-frame memset of the (capacity x 52 B) table sits on the critical path.
 #include "apc_scan.cuh"
+APC_TRACE_EXPORT(voxel)
 
 #define VOX_EMPTY 0xffffffffffffffffull
 #define VOX_NOSLOT 0xffffffffu
@@ -36,6 +37,7 @@ k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
                VoxSlot* __restrict__ slots, uint32_t cap_mask, uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t stride = gridDim.x * blockDim.x;
+  APC_STAMP(0, 0);
   for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * VOX_ILP) {
     float4 p[VOX_ILP];
     uint64_t key[VOX_ILP];
@@ -88,6 +90,7 @@ k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
       atomicAdd(&s->acc[3], (unsigned long long)qi);
     }
   }
+  APC_STAMP(0, 1);
 }
 
 __device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, double inv_scale) {
@@ -105,6 +108,7 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
   const uint32_t tile = blockIdx.x;
   bool is_first[APC_TILE_ITEMS];
   uint32_t slot[APC_TILE_ITEMS];
+  APC_STAMP(1, 0);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
@@ -116,7 +120,9 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
     }
   }
   uint32_t rank[APC_TILE_ITEMS];
+  APC_STAMP(1, 1);
   const uint32_t base = tile_compact_offsets(is_first, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+  APC_STAMP(1, 2);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     if (is_first[j]) {
@@ -139,6 +145,7 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
       raw[2] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
+  APC_STAMP(1, 3);
 }
 
 __global__ void k_voxel_p2v(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
