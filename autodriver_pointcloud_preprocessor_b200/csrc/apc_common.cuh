@@ -23,12 +23,18 @@ enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
 // One voxel of the open-addressing table.  Everything a point touches when it is inserted
 // (key CAS, first-index min, count, four fixed-point sums) sits in one aligned 64-byte
 // half-line = two 32-byte L2 sectors, instead of five lines of five separate arrays.
+// The point whose CAS claims the slot (the "owner") touches nothing else: it records its index
+// with a plain store and its coordinates are added when the voxel is finalised.  Only the points
+// that JOIN an existing voxel pay the six accumulating atomics - at 0.1 m on a 262k-point scan 77 %
+// of the voxels hold a single point, so a scan issues ~0.7 M atomics instead of 1.8 M (the insert
+// kernel is bound by the SM's ~1.3 cycles/lane issue rate for scattered atomics).
 struct __align__(64) VoxSlot {
   unsigned long long key;     // packed 63-bit voxel key, all ones = empty
-  uint32_t first;             // lowest point index in the voxel
-  uint32_t cnt;               // points in the voxel
-  unsigned long long acc[4];  // fixed-point sums: x, y, z (2^-24 m), intensity (2^-20)
-  unsigned long long pad[2];
+  uint32_t first;             // lowest index among the JOINING points (0xffffffff: none)
+  uint32_t cnt;               // number of joining points (the owner is not counted)
+  unsigned long long acc[4];  // fixed-point sums over the joining points: x, y, z (2^-24 m), intensity (2^-20)
+  uint32_t owner;             // index of the point that claimed the slot
+  uint32_t pad[3];
 };
 static_assert(sizeof(VoxSlot) == 64, "VoxSlot must be one 64-byte half line");
 
@@ -143,11 +149,11 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
   uint64_t v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // "Last CTA" ticket: called by ONE thread after a __syncthreads().  The acq_rel RMW at gpu scope

@@ -111,12 +111,16 @@ struct TilePoint {
 // Loads the striped tile `tile_local` of segment `s`: item j of thread t is point
 // tile_local*1024 + j*256 + t.  `stage` is dynamic shared memory (>= 1024*step bytes,
 // 16-byte aligned) used only by the generic path; `bar` a shared mbarrier.
+// GENERIC = false compiles the FAST16 path only (the host launches that instantiation when every
+// segment qualifies): the byte-record decoder is a lot of code, and keeping it out of the common
+// kernel keeps the hot loop inside the instruction cache.
+template <bool GENERIC>
 __device__ __forceinline__ void load_tile(const SegDev& s, uint32_t tile_local, bool test_nan,
                                           uint8_t* stage, uint64_t* bar,
                                           TilePoint (&pt)[APC_TILE_ITEMS]) {
   const uint32_t first = tile_local * APC_TILE_POINTS;
   const uint32_t in_tile = min(APC_TILE_POINTS, s.n - first);
-  if (s.fast16) {
+  if (!GENERIC || s.fast16) {
     const float4* src = reinterpret_cast<const float4*>(s.data) + first;
 #pragma unroll
     for (int j = 0; j < APC_TILE_ITEMS; ++j) {
@@ -137,6 +141,7 @@ __device__ __forceinline__ void load_tile(const SegDev& s, uint32_t tile_local, 
     }
     return;
   }
+  if (!GENERIC) return;
   // ---- generic: stage the tile's bytes in shared memory --------------------------------
   const uint8_t* gsrc = s.data + (size_t)first * s.step;
   const uint32_t bytes = in_tile * s.step;

@@ -1,10 +1,12 @@
 // Single-pass order-preserving stream compaction building blocks:
-// warp-ballot ranks inside a tile + decoupled look-back across tiles.
+// warp-ballot ranks inside a tile + a two-level cross-tile scan.
 //
-// Tile state word (one uint64 per tile, never cleared between launches):
+// Scan state (uint64 words, never cleared between launches):
 //   [63:34] epoch of the API call that wrote it  [33:32] status  [31:0] value
 // A word whose epoch differs from the current one reads as "not ready", so the state array
 // needs no memset per launch (one less node on the latency-critical path).
+//   words [0, APC_SCAN_GROUPS)       group aggregates: sum of the totals of 32 consecutive tiles
+//   words [APC_SCAN_GROUPS + t]      total of tile t
 #pragma once
 #include "apc_common.cuh"
 
@@ -12,50 +14,54 @@
 #define APC_TILE_ITEMS 4
 #define APC_TILE_POINTS (APC_TILE_THREADS * APC_TILE_ITEMS)  // 1024 points per CTA
 
-enum { APC_ST_INVALID = 0u, APC_ST_AGGREGATE = 1u, APC_ST_PREFIX = 2u };
+enum { APC_ST_INVALID = 0u, APC_ST_VALID = 1u };
+#define APC_SCAN_GROUP 32u          // tiles per group
+#define APC_SCAN_GROUPS 1024u       // group words reserved at the front of a state array (32M points)
 
 __device__ __forceinline__ uint64_t scan_pack(uint32_t epoch, uint32_t status, uint32_t value) {
   return ((uint64_t)(epoch & 0x3fffffffu) << 34) | ((uint64_t)status << 32) | value;
 }
+// spins until the word carries the current epoch; returns its value
+__device__ __forceinline__ uint32_t scan_wait(const uint64_t* word, uint32_t ep) {
+  uint64_t w = ld_volatile_u64(word);
+  while ((uint32_t)(w >> 34) != ep) w = ld_volatile_u64(word);
+  return (uint32_t)w;
+}
 
-// Called by warp 0 of the CTA (all 32 lanes).  Publishes this tile's aggregate, walks back
-// over predecessor tiles 32 at a time and returns the exclusive prefix (same value in all
-// lanes).  Relies on CTAs being dispatched in blockIdx order (as CUB's scan does).
-__device__ __forceinline__ uint32_t scan_lookback(uint64_t* __restrict__ state, uint32_t tile,
-                                                  uint32_t epoch, uint32_t aggregate) {
-  const uint32_t lane = lane_id();
+// Exclusive prefix of this tile's `total` over all lower-numbered tiles, two levels deep:
+//   1. the tile publishes its total;
+//   2. warp 0 reads the totals of the earlier tiles of its own 32-tile group (one coalesced load,
+//      lane i <- tile i of the group); the group's last tile also publishes the group aggregate;
+//   3. warp 0 reads the aggregates of all earlier groups (lane g <- group g).
+// Two dependent round trips after the publish, O(1) polled words per tile.  Measured on a
+// 256-tile launch (profiles/cta_trace.py): ~4 us, against ~8 us for a 256-wide look-back window
+// (65k polling threads queue up on 16 L2 lines) and ~7 us for reading all earlier totals directly
+// (n^2/2 polled words): what costs is the number of threads polling the same lines.
+// Called by all threads of the CTA; relies on CTAs being dispatched in blockIdx order (lower
+// tiles are resident or finished whenever a tile waits).  smem: one uint32_t.
+__device__ __forceinline__ uint32_t scan_two_level(uint64_t* __restrict__ state, uint32_t tile, uint32_t n_tiles,
+                                                   uint32_t epoch, uint32_t total, uint32_t* smem1) {
   const uint32_t ep = epoch & 0x3fffffffu;
-  if (tile == 0) {
-    if (lane == 0) st_volatile_u64(&state[0], scan_pack(ep, APC_ST_PREFIX, aggregate));
-    return 0;
-  }
-  if (lane == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_AGGREGATE, aggregate));
-  uint32_t exclusive = 0;
-  int32_t base = (int32_t)tile - 1;
-  while (true) {
-    const int32_t idx = base - (int32_t)lane;
-    uint32_t status, value;
-    do {
-      if (idx >= 0) {
-        const uint64_t w = ld_volatile_u64(&state[idx]);
-        status = ((uint32_t)(w >> 34) == ep) ? (uint32_t)((w >> 32) & 3u) : APC_ST_INVALID;
-        value = (uint32_t)w;
-      } else {  // before tile 0: behaves as a prefix of zero
-        status = APC_ST_PREFIX;
-        value = 0;
-      }
-    } while (__any_sync(0xffffffffu, status == APC_ST_INVALID));
-    const uint32_t pmask = __ballot_sync(0xffffffffu, status == APC_ST_PREFIX);
-    if (pmask) {
-      const uint32_t first = __ffs(pmask) - 1;  // nearest predecessor holding a full prefix
-      exclusive += warp_sum_u32(lane <= first ? value : 0u);
-      break;
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t group = tile / APC_SCAN_GROUP, r = tile % APC_SCAN_GROUP;
+    uint64_t* totals = state + APC_SCAN_GROUPS;
+    if (lane == 0) st_volatile_u64(&totals[tile], scan_pack(ep, APC_ST_VALID, total));
+    uint32_t v = 0;
+    if (lane < r) v = scan_wait(&totals[group * APC_SCAN_GROUP + lane], ep);
+    const uint32_t in_group = warp_sum_u32(v);
+    const uint32_t last = min(group * APC_SCAN_GROUP + APC_SCAN_GROUP - 1u, n_tiles - 1u);
+    if (tile == last && lane == 0) st_volatile_u64(&state[group], scan_pack(ep, APC_ST_VALID, in_group + total));
+    uint32_t before = 0;
+    for (uint32_t g0 = 0; g0 < group; g0 += 32) {
+      uint32_t u = 0;
+      if (g0 + lane < group) u = scan_wait(&state[g0 + lane], ep);
+      before += warp_sum_u32(u);
     }
-    exclusive += warp_sum_u32(value);
-    base -= 32;
+    if (lane == 0) *smem1 = before + in_group;
   }
-  if (lane == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_PREFIX, exclusive + aggregate));
-  return exclusive;
+  __syncthreads();
+  return *smem1;
 }
 
 // Order-preserving ranks for a striped tile: item j of thread t is tile element j*256+t.
@@ -92,62 +98,7 @@ __device__ __forceinline__ uint32_t tile_ranks(const bool (&keep)[APC_TILE_ITEMS
 }
 static_assert(APC_TILE_ITEMS * (APC_TILE_THREADS / 32) == 32, "tile_ranks scans exactly 32 warp totals");
 
-// CTA-wide decoupled look-back: the whole CTA inspects a window of 256 predecessor tiles at
-// once (thread i looks at tile base-i), so a scan of <= 256 tiles - every per-scan launch at
-// 262k points - resolves in ONE round of independent loads instead of up to 8 dependent
-// 32-wide rounds by a single warp.  Called by all 256 threads; smem: uint32_t[34] (shared with
-// tile_ranks: slots 0..15 are reused here after the ranks have been read).
-__device__ __forceinline__ uint32_t scan_lookback_cta(uint64_t* __restrict__ state, uint32_t tile, uint32_t epoch,
-                                                      uint32_t aggregate, uint32_t* smem34) {
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint32_t ep = epoch & 0x3fffffffu;
-  if (tile == 0) {
-    if (threadIdx.x == 0) st_volatile_u64(&state[0], scan_pack(ep, APC_ST_PREFIX, aggregate));
-    return 0;
-  }
-  if (threadIdx.x == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_AGGREGATE, aggregate));
-  __syncthreads();  // every thread has finished reading the rank scratch in smem34
-  uint32_t exclusive = 0;
-  int32_t base = (int32_t)tile - 1;
-  while (true) {
-    const int32_t idx = base - (int32_t)threadIdx.x;
-    uint32_t status, value;
-    do {
-      if (idx >= 0) {
-        const uint64_t w = ld_volatile_u64(&state[idx]);
-        status = ((uint32_t)(w >> 34) == ep) ? (uint32_t)((w >> 32) & 3u) : APC_ST_INVALID;
-        value = (uint32_t)w;
-      } else {
-        status = APC_ST_PREFIX;
-        value = 0;
-      }
-    } while (__any_sync(0xffffffffu, status == APC_ST_INVALID));
-    // per warp: sum of the values up to and including its nearest full prefix (or all 32)
-    const uint32_t pmask = __ballot_sync(0xffffffffu, status == APC_ST_PREFIX);
-    const uint32_t first = pmask ? (uint32_t)__ffs(pmask) - 1u : 31u;
-    const uint32_t wsum = warp_sum_u32(lane <= first ? value : 0u);
-    if (lane == 0) {
-      smem34[warp] = wsum;
-      smem34[8 + warp] = pmask ? 1u : 0u;
-    }
-    __syncthreads();
-    bool found = false;
-#pragma unroll
-    for (int w = 0; w < APC_TILE_THREADS / 32; ++w) {  // warps in order of increasing distance
-      if (!found) {
-        exclusive += smem34[w];
-        found = smem34[8 + w] != 0u;
-      }
-    }
-    __syncthreads();
-    if (found) break;
-    base -= APC_TILE_THREADS;
-  }
-  if (threadIdx.x == 0) st_volatile_u64(&state[tile], scan_pack(ep, APC_ST_PREFIX, exclusive + aggregate));
-  return exclusive;
-}
-
-// Full tile step: ranks + look-back.  Returns the global exclusive offset of this tile in
+// Full tile step: ranks + cross-tile scan.  Returns the global exclusive offset of this tile in
 // `tile_base` (all threads) and leaves per-item ranks in rank[].  smem: uint32_t[34].
 __device__ __forceinline__ uint32_t tile_compact_offsets(const bool (&keep)[APC_TILE_ITEMS],
                                                          uint32_t (&rank)[APC_TILE_ITEMS],
@@ -155,7 +106,7 @@ __device__ __forceinline__ uint32_t tile_compact_offsets(const bool (&keep)[APC_
                                                          uint32_t tile, uint32_t epoch,
                                                          uint32_t* total_out, uint32_t n_tiles) {
   const uint32_t total = tile_ranks(keep, rank, smem34);
-  const uint32_t excl = scan_lookback_cta(state, tile, epoch, total, smem34);
+  const uint32_t excl = scan_two_level(state, tile, n_tiles, epoch, total, &smem34[33]);
   if (threadIdx.x == 0 && tile == n_tiles - 1 && total_out) *total_out = excl + total;
   return excl;
 }

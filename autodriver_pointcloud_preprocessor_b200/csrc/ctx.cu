@@ -6,6 +6,7 @@
 #include "apc_common.cuh"
 
 static thread_local std::string g_create_error;
+APC_TRACE_EXPORT(ctx)
 
 
 
@@ -33,6 +34,7 @@ int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce) {
 }
 
 __global__ void k_begin(ApcCtrl* ctrl) {
+  APC_STAMP(0, 0);
   if (threadIdx.x == 0) ctrl->epoch = ctrl->epoch + 1u;
   if (threadIdx.x < 30) ctrl->counters[threadIdx.x] = 0u;
 }
@@ -102,7 +104,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
     return APC_ERR_CUDA;                                                \
   }
   A(dalloc(&ctx->ctrl, 1));
-  for (auto& p : ctx->scan_state) A(dalloc(&p, ctx->max_tiles));
+  for (auto& p : ctx->scan_state) A(dalloc(&p, (size_t)ctx->max_tiles + 1024));   // + APC_SCAN_GROUPS group words
   A(dalloc(&ctx->vox_slots, C));
   A(dalloc(&ctx->vox_rank, C));
   A(dalloc(&ctx->p2slot, M));
@@ -126,7 +128,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   A(dalloc(&ctx->idx_a, M));
   A(dalloc(&ctx->dev_counts, 16));
   A(cudaMemset(ctx->ctrl, 0, sizeof(ApcCtrl)));
-  for (auto& p : ctx->scan_state) A(cudaMemset(p, 0, ctx->max_tiles * sizeof(uint64_t)));
+  for (auto& p : ctx->scan_state) A(cudaMemset(p, 0, ((size_t)ctx->max_tiles + 1024) * sizeof(uint64_t)));
   A(cudaMemset(ctx->dev_counts, 0, 16 * sizeof(uint32_t)));
   if (reset_tables(ctx, 0) != APC_OK) {
     g_create_error = ctx->err;

@@ -40,16 +40,13 @@ struct FrontendParams {
 // reading the representative's coordinates back from the input (only real duplicates and 2^-32
 // fingerprint collisions get there).  Equal keys then lower the index with atomicMin (same
 // fingerprint in the high half, so the minimum is the lower index).
-//
-// Probing is bucketised: a key's home is a 32-byte bucket of 4 slots (one L2 sector).  An insert
-// reads the whole bucket with one 2 x 128-bit load, picks the first slot that is empty or holds
-// its key, and issues ONE compare-and-swap - two dependent round trips whatever the probe length,
-// where slot-by-slot linear probing paid one atomic round trip per probe (profiled: the warp-wide
-// worst probe chain, not atomic throughput, was what made this kernel 38 us).  Slots of a bucket
-// fill strictly left to right and nothing is deleted while inserts run, so "first empty slot"
-// implies that every earlier insert of the same key is already visible to the scan.
+// Probing: compare-and-swap first, linear, all the items of a thread in lockstep so that their
+// atomic round trips overlap (a thread's latency is the longest of its probe chains, not their
+// sum).  Measured at 262k points (eager, CUDA events): 8 us with no table access at all, 10 us for
+// one CAS per point, 16 us for this kernel; a variant that first read a 4-slot bucket with
+// ld.global.cg and then CASed the first free slot took 33 us - concurrent inserts see the same
+// free slot and lose the race, and the re-read can be served a stale copy.
 #define DEDUP_EMPTY 0xffffffffffffffffull
-#define DEDUP_BUCKET 4u
 
 __device__ __forceinline__ uint64_t dedup_hash(float x, float y, float z) {
   const uint32_t kx = __float_as_uint(x), ky = __float_as_uint(y), kz = __float_as_uint(z);
@@ -59,85 +56,75 @@ __device__ __forceinline__ unsigned long long dedup_word(uint64_t h, uint32_t g)
   return ((unsigned long long)(h >> 32) << 32) | g;   // never all ones: g is a valid point index
 }
 
-// Inserts ITEMS points per thread in lockstep: the bucket loads of all unfinished items are in
-// flight together, then their compare-and-swaps.  slot_mask = capacity - 1 (capacity a multiple of
-// the bucket size); `same(j, rep)` tells whether point `rep` has item j's x/y/z bit patterns.
+// Inserts ITEMS points per thread.  `same(j, rep)` tells whether point `rep` has item j's x/y/z
+// bit patterns (called on fingerprint hits only).
 template <int ITEMS, typename SameFn>
 __device__ __forceinline__ void dedup_insert_items(unsigned long long* slots, uint32_t slot_mask, uint32_t* p2slot,
                                                    ApcCtrl* ctrl, const uint64_t (&hash)[ITEMS],
                                                    const unsigned long long (&word)[ITEMS], bool (&act)[ITEMS], SameFn same) {
-  uint32_t bucket[ITEMS], tries[ITEMS];
+  uint32_t slot[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) { bucket[j] = (uint32_t)hash[j] & slot_mask & ~(DEDUP_BUCKET - 1u); tries[j] = 0; }
-  bool any = false;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) any |= act[j];
-  while (any) {
-    ulonglong2 lo[ITEMS], hi[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (act[j]) {   // L2 loads (.cg): a stale L1 line could hide a slot another SM has just filled
-        lo[j] = __ldcg(reinterpret_cast<const ulonglong2*>(slots + bucket[j]));
-        hi[j] = __ldcg(reinterpret_cast<const ulonglong2*>(slots + bucket[j]) + 1);
-      }
-    int want[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      want[j] = -1;
-      if (!act[j]) continue;
-      const unsigned long long v[4] = {lo[j].x, lo[j].y, hi[j].x, hi[j].y};
-      bool done = false;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (done || want[j] >= 0) continue;
-        if (v[k] == DEDUP_EMPTY) { want[j] = k; continue; }
-        if ((v[k] >> 32) == (word[j] >> 32) && same(j, (uint32_t)v[k])) {
-          if ((uint32_t)word[j] < (uint32_t)v[k]) atomicMin(&slots[bucket[j] + k], word[j]);   // lower the index
-          p2slot[(uint32_t)word[j]] = bucket[j] + k;
-          done = true;
-        }
-      }
-      if (done) { act[j] = false; continue; }
-      if (want[j] < 0) {   // bucket full of other keys: next bucket
-        bucket[j] = (bucket[j] + DEDUP_BUCKET) & slot_mask;
-        if (++tries[j] > (slot_mask >> 2)) {
-          atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-          p2slot[(uint32_t)word[j]] = 0;
-          act[j] = false;
-        }
-      }
-    }
+  for (int j = 0; j < ITEMS; ++j) slot[j] = (uint32_t)hash[j] & slot_mask;
+  for (uint32_t probe = 0; probe <= slot_mask; ++probe) {
     unsigned long long old[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j)
-      if (act[j] && want[j] >= 0) old[j] = atomicCAS(&slots[bucket[j] + want[j]], DEDUP_EMPTY, word[j]);
-    any = false;
+    for (int j = 0; j < ITEMS; ++j)   // issue every unfinished item's CAS before looking at any result
+      old[j] = act[j] ? atomicCAS(&slots[slot[j]], DEDUP_EMPTY, word[j]) : 0ull;
+    bool any = false;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-      if (act[j] && want[j] >= 0 && old[j] == DEDUP_EMPTY) {
-        p2slot[(uint32_t)word[j]] = bucket[j] + want[j];
+      if (!act[j]) continue;
+      bool done = old[j] == DEDUP_EMPTY;
+      if (!done && (old[j] >> 32) == (word[j] >> 32) && same(j, (uint32_t)old[j])) {
+        if ((uint32_t)word[j] < (uint32_t)old[j]) atomicMin(&slots[slot[j]], word[j]);   // a later point got here first
+        done = true;
+      }
+      if (done) {
+        p2slot[(uint32_t)word[j]] = slot[j];
         act[j] = false;
-      }   // a lost race re-reads the same bucket on the next round
-      any |= act[j];
+      } else {
+        slot[j] = (slot[j] + 1) & slot_mask;
+        any = true;
+      }
     }
+    if (!any) return;
   }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    if (act[j]) {
+      atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+      p2slot[(uint32_t)word[j]] = 0;
+    }
 }
 
 // x/y/z of point `g` of the launch, straight from the byte records (the confirm step above)
-template <typename P>
+template <bool GENERIC, typename P>
 __device__ __forceinline__ void load_xyz_global(const P& prm, uint32_t g, float& x, float& y, float& z) {
   uint32_t si = 0;
 #pragma unroll
   for (uint32_t k = 1; k < APC_MAX_CLOUDS; ++k)
     if (k < prm.n_seg && g >= prm.seg[k].point_begin) si = k;
   const SegDev& s = prm.seg[si];
+  if (!GENERIC) {   // FAST16: x, y, z are the first three floats of a 16-byte record
+    const float4 v = __ldg(reinterpret_cast<const float4*>(s.data) + (g - s.point_begin));
+    x = v.x; y = v.y; z = v.z;
+    return;
+  }
   const uint8_t* rec = s.data + (size_t)(g - s.point_begin) * s.step;
   x = field_as_f32(rec + s.off[0], s.dt[0]);
   y = field_as_f32(rec + s.off[1], s.dt[1]);
   z = field_as_f32(rec + s.off[2], s.dt[2]);
 }
 
+template <bool GENERIC>
+__device__ __noinline__ bool dedup_same_record(const FrontendParams& prm, uint32_t rep, uint32_t kx, uint32_t ky, uint32_t kz) {
+  float rx, ry, rz;
+  load_xyz_global<GENERIC>(prm, rep, rx, ry, rz);
+  return __float_as_uint(rx) == kx && __float_as_uint(ry) == ky && __float_as_uint(rz) == kz;
+}
+
 // Pass 1 of duplicate removal over the raw byte buffers.
+template <bool GENERIC>
 __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_constant__ FrontendParams prm) {
   extern __shared__ __align__(16) uint8_t stage[];
   __shared__ __align__(8) uint64_t bar;
@@ -146,7 +133,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_
   const SegDev& s = prm.seg[si];
   TilePoint pt[APC_TILE_ITEMS];
   APC_STAMP(0, 0);
-  load_tile(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
+  load_tile<GENERIC>(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
   if (pt[0].x == 123456.f) APC_STAMP(0, 3);   // data dependence: the stamp below follows the loads
   APC_STAMP(0, 1);
   uint64_t hash[APC_TILE_ITEMS];
@@ -159,12 +146,11 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_
     hash[j] = dedup_hash(pt[j].x, pt[j].y, pt[j].z);
     word[j] = dedup_word(hash[j], g0 + j * APC_TILE_THREADS);
   }
+  // fingerprint hits are confirmed out of line (rare; keeps the probe loop small: inlined into
+  // every probe the byte-record decoder made this kernel 190 KB of SASS)
   dedup_insert_items<APC_TILE_ITEMS>(prm.slots, prm.slot_mask, prm.p2slot, prm.ctrl, hash, word, act,
                                      [&](int j, uint32_t rep) {
-    float rx, ry, rz;
-    load_xyz_global(prm, rep, rx, ry, rz);
-    return __float_as_uint(rx) == __float_as_uint(pt[j].x) && __float_as_uint(ry) == __float_as_uint(pt[j].y) &&
-           __float_as_uint(rz) == __float_as_uint(pt[j].z);
+    return dedup_same_record<GENERIC>(prm, rep, __float_as_uint(pt[j].x), __float_as_uint(pt[j].y), __float_as_uint(pt[j].z));
   });
   APC_STAMP(0, 2);
 }
@@ -187,6 +173,7 @@ __device__ __forceinline__ bool crop_keep(const FrontendParams& prm, float x, fl
   return prm.crop_mode == APC_CROP_OPEN3D ? !in_all : out_any;
 }
 
+template <bool GENERIC>
 __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_constant__ FrontendParams prm) {
   extern __shared__ __align__(16) uint8_t stage[];
   __shared__ __align__(8) uint64_t bar;
@@ -197,7 +184,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
   const uint32_t epoch = prm.ctrl->epoch;
   TilePoint pt[APC_TILE_ITEMS];
   APC_STAMP(1, 0);
-  load_tile(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
+  load_tile<GENERIC>(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
 
   bool keep[APC_TILE_ITEMS];
   uint32_t gidx[APC_TILE_ITEMS];
@@ -369,8 +356,8 @@ static int set_smem(apc_ctx* ctx, uint32_t smem) {
   static uint32_t configured = 0;  // both kernels share the limit; opt in once
   // static shared memory counts against the 48 KB default too, so opt in well below it
   if (smem > 32 * 1024 && smem > configured) {
-    APC_CUDA(ctx, cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
-    APC_CUDA(ctx, cudaFuncSetAttribute(k_dedup_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
+    APC_CUDA(ctx, cudaFuncSetAttribute(k_frontend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
+    APC_CUDA(ctx, cudaFuncSetAttribute(k_dedup_insert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
     configured = 192 * 1024;
   }
   return APC_OK;
@@ -397,13 +384,16 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
   APC_REQUIRE(ctx, prm.n_tiles <= ctx->max_tiles, "too many tiles for this context");
   rc = set_smem(ctx, smem);
   if (rc) return rc;
+  const bool generic = smem != 0;   // some segment needs the byte-record decoder
   if (prm.dedup) {
     APC_PROF(ctx, "k_dedup_insert", s);
-    k_dedup_insert<<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
+    if (generic) k_dedup_insert<true><<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
+    else k_dedup_insert<false><<<prm.n_tiles, APC_TILE_THREADS, 0, s>>>(prm);
     APC_LAUNCH_CHECK(ctx, "k_dedup_insert");
   }
   APC_PROF(ctx, "k_frontend", s);
-  k_frontend<<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
+  if (generic) k_frontend<true><<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
+  else k_frontend<false><<<prm.n_tiles, APC_TILE_THREADS, 0, s>>>(prm);
   APC_LAUNCH_CHECK(ctx, "k_frontend");
   return APC_OK;
 }

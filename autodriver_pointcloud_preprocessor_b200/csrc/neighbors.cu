@@ -51,24 +51,13 @@ __device__ __forceinline__ uint64_t grid_key(uint32_t level, int32_t ix, int32_t
   return ((uint64_t)level << 57) | ((uint64_t)(uint32_t)(ix + 262144) << 38) |
          ((uint64_t)(uint32_t)(iy + 262144) << 19) | (uint64_t)(uint32_t)(iz + 262144);
 }
-// Probing is bucketised like the duplicate table (frontend.cu): a key's home is a 32-byte bucket
-// of 4 key words read with one 2 x 128-bit load; buckets fill left to right and nothing is removed
-// while a grid is in use, so a lookup stops at the first empty word.
-#define GRID_BUCKET 4u
 __device__ __forceinline__ uint32_t grid_find(const GridDev& g, uint64_t key) {
-  uint32_t b = (uint32_t)mix64(key) & g.cap_mask & ~(GRID_BUCKET - 1u);
-  for (uint32_t tries = 0; tries <= (g.cap_mask >> 2); ++tries) {
-    const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(g.keys + b);
-    const ulonglong2 hi = *(reinterpret_cast<const ulonglong2*>(g.keys + b) + 1);
-    if (lo.x == key) return b;
-    if (lo.x == GRID_EMPTY) return GRID_NOSLOT;
-    if (lo.y == key) return b + 1;
-    if (lo.y == GRID_EMPTY) return GRID_NOSLOT;
-    if (hi.x == key) return b + 2;
-    if (hi.x == GRID_EMPTY) return GRID_NOSLOT;
-    if (hi.y == key) return b + 3;
-    if (hi.y == GRID_EMPTY) return GRID_NOSLOT;
-    b = (b + GRID_BUCKET) & g.cap_mask;
+  uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
+  for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
+    const unsigned long long k = g.keys[s];
+    if (k == key) return s;
+    if (k == GRID_EMPTY) return GRID_NOSLOT;
+    s = (s + 1) & g.cap_mask;
   }
   return GRID_NOSLOT;
 }
@@ -79,26 +68,18 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
   const float c = g.cell[level];
+  APC_STAMP(1, 0);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
     int32_t ix, iy, iz;
     uint32_t slot = GRID_NOSLOT, rank = 0;
     if (grid_coord(p.x, p.y, p.z, c, ix, iy, iz)) {
-      const unsigned long long key = grid_key(level, ix, iy, iz);
-      uint32_t b = (uint32_t)mix64(key) & g.cap_mask & ~(GRID_BUCKET - 1u);
-      for (uint32_t tries = 0; slot == GRID_NOSLOT && tries <= (g.cap_mask >> 2); ++tries) {
-        // one L2 read of the bucket (.cg: never a stale L1 copy), then at most one CAS per slot
-        const ulonglong2 lo = __ldcg(reinterpret_cast<const ulonglong2*>(g.keys + b));
-        const ulonglong2 hi = __ldcg(reinterpret_cast<const ulonglong2*>(g.keys + b) + 1);
-        const unsigned long long v[4] = {lo.x, lo.y, hi.x, hi.y};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (slot != GRID_NOSLOT) continue;
-          unsigned long long cur = v[k];
-          if (cur == GRID_EMPTY) cur = atomicCAS(&g.keys[b + k], GRID_EMPTY, key);   // the occupant if the race is lost
-          if (cur == GRID_EMPTY || cur == key) slot = b + k;
-        }
-        b = (b + GRID_BUCKET) & g.cap_mask;
+      const uint64_t key = grid_key(level, ix, iy, iz);
+      uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
+      for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
+        const unsigned long long old = atomicCAS(&g.keys[s], GRID_EMPTY, (unsigned long long)key);
+        if (old == GRID_EMPTY || old == key) { slot = s; break; }
+        s = (s + 1) & g.cap_mask;
       }
       if (slot == GRID_NOSLOT) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
       else rank = atomicAdd(&g.fill[slot], 1u);
@@ -108,6 +89,7 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
     g.slot[(size_t)level * n_max + i] = slot;
     g.rank[(size_t)level * n_max + i] = rank;
   }
+  APC_STAMP(1, 1);
 }
 
 // rank-0 points reserve a contiguous run for their cell (warp-aggregated cursor bump)
@@ -117,6 +99,7 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
   const uint32_t level = blockIdx.y;
   const uint32_t lane = lane_id();
   const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  APC_STAMP(2, 0);
   for (uint32_t r = 0; r < rounds; ++r) {
     const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     uint32_t slot = GRID_NOSLOT, cnt = 0;
@@ -136,12 +119,14 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
     base = __shfl_sync(0xffffffffu, base, 31);
     if (cnt) g.start[slot] = base + incl - cnt;
   }
+  APC_STAMP(2, 1);
 }
 
 __global__ void __launch_bounds__(256)
 k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
+  APC_STAMP(3, 0);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = g.slot[(size_t)level * n_max + i];
     if (slot == GRID_NOSLOT) continue;
@@ -149,11 +134,13 @@ k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
     g.sorted[(size_t)level * n_max + g.start[slot] + g.rank[(size_t)level * n_max + i]] =
         make_float4(p.x, p.y, p.z, __uint_as_float(i));
   }
+  APC_STAMP(3, 1);
 }
 
 __global__ void __launch_bounds__(256) k_grid_clean(uint32_t n_max, const uint32_t* n_dev, GridDev g) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
+  APC_STAMP(4, 0);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = g.slot[(size_t)level * n_max + i];
     if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) {
@@ -161,6 +148,7 @@ __global__ void __launch_bounds__(256) k_grid_clean(uint32_t n_max, const uint32
       g.fill[slot] = 0u;
     }
   }
+  APC_STAMP(4, 1);
 }
 
 __global__ void k_grid_reset(unsigned long long* keys, uint32_t* fill, uint32_t cap) {
@@ -532,7 +520,10 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   GridHost& g = scratch_of(ctx)->grid[0];
   const float r32 = (float)radius;
   const float r2 = r32 * r32;                       // float32(r)^2, rounded once
-  const float cell = r32 * 1.0009765625f;           // slack so that d2 <= r2 never reaches 2 cells away
+  // cells of r (+ slack, so that d2 <= r2 never reaches 2 cells away); measured alternatives at
+  // 200k points: cells of 2r 37 us, one warp per cell group with shuffled broadcasts 85 us,
+  // neighbour-cell lookups issued in rounds of 6-13 32-50 us, this per-thread walk 29-32 us
+  const float cell = r32 * 1.0009765625f;
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
   if (rc) return rc;

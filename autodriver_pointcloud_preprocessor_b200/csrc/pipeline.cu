@@ -3,6 +3,7 @@
 // counters so that no stage waits for the host, plus CUDA-graph capture / replay of the
 // whole chain (one launch per scan).
 #include "apc_common.cuh"
+APC_TRACE_EXPORT(pipeline)
 
 // stage entry points without the per-call epoch bump (defined in the stage files)
 int apc_frontend_nobegin(apc_ctx*, const apc_cloud_desc*, uint32_t, const apc_filter_cfg*, float*, uint32_t*, uint8_t*,
@@ -32,6 +33,7 @@ __global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t
   out[APC_CNT_GROUND_INLIERS] = has_ground ? dc[DC_INFO + 1] : 0u;
   out[APC_CNT_OUTPUT] = dc[last];
   out[APC_CNT_STATUS] = ctrl->err;
+  APC_STAMP(0, 0);
 }
 
 static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds, const apc_pipeline_cfg* cfg,

@@ -12,6 +12,7 @@
 //   - final pass: inlier mask against the winning hypothesis + moment sums for the
 //     least-squares refit, reduced in a fixed order.
 #include "apc_scan.cuh"
+APC_TRACE_EXPORT(ransac)
 
 #define RS_CHUNK 16
 #define RS_MAX_N 16
@@ -200,6 +201,7 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   const uint32_t nh = min((uint32_t)CH, iters - h0);
   const uint32_t tid = threadIdx.x;
   RS_STAMP(0);
+  APC_STAMP(0, 0);
 #ifdef RS_TRACE
   if (threadIdx.x == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_rs_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = sm; }
 #endif
@@ -359,9 +361,11 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   if (tid == 0) s_last = (ticket_acq_rel(&ctrl->counters[CTR_RS_SCORE_TICKET]) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   RS_STAMP(4);
+  APC_STAMP(0, 1);
   if (!s_last) return;
   rs_select_cta(planes, scores, gridDim.x, gridDim.y * CH, P, ransac_n, iters, prob, plane8, info, scores_copy);
   RS_STAMP(5);
+  APC_STAMP(0, 2);
 }
 
 // Open3D's sequential selection + early-stop rule over the batched scores, run by one CTA.
@@ -496,6 +500,7 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   __shared__ bool s_last;
   __shared__ uint32_t sm_scan[34];
   const uint32_t P = apc_count(n_dev, n_max);
+  APC_STAMP(1, 0);
   const bool have = info[0] != 0xffffffffu;
   const double pl[4] = {plane8[4], plane8[5], plane8[6], plane8[7]};
   double acc[10];
@@ -545,6 +550,7 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   __syncthreads();
   if (threadIdx.x == 0) s_last = (ticket_acq_rel(&ctrl->counters[CTR_RS_TICKET]) == gridDim.x - 1);
   __syncthreads();
+  APC_STAMP(1, 1);
   if (!s_last) return;
   // last CTA: stage 256 partial rows at a time in shared memory (parallel, coalesced loads),
   // then thread k < 10 adds moment k in CTA order
@@ -571,6 +577,7 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     const double yy = s_tot[7] - n * cy * cy, yz = s_tot[8] - n * cy * cz, zz = s_tot[9] - n * cz * cz;
     plane_from_moments(cx, cy, cz, xx, xy, xz, yy, yz, zz, plane8);
   }
+  APC_STAMP(1, 2);
 }
 
 int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, double thr,

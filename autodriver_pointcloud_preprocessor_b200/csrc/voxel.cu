@@ -5,7 +5,8 @@
 //   table     = open addressing, linear probing, 64-bit atomicCAS on the key word
 //   centroid  = order-independent fixed-point sums (rint(x*2^24), 64-bit integer atomics) so
 //               the result is deterministic and bit-identical to oracle/voxel.py
-//               centroids_fixed whatever order the atomics land in
+//               centroids_fixed whatever order the atomics land in; the point that claims a
+//               slot adds nothing atomically (see VoxSlot)
 //   order     = first-occurrence: a point is "first" when it holds the lowest index of its
 //               slot; an order-preserving scan over the first-flags numbers the voxels
 // The table is self-cleaning: the thread that finalises a voxel resets its slot, so no
@@ -28,66 +29,53 @@ __device__ __forceinline__ bool voxel_key(float4 p, float vs, uint64_t& key) {
   return true;
 }
 
-// VOX_ILP = points per thread per round.  Measured on B200 at 262k points: 1 -> 25 us,
-// 2 -> 28 us, 4 -> 35 us (more points in flight per thread = fewer resident warps to hide the
-// dependent atomic chain), so the kernel runs with 1.
-#define VOX_ILP 1
+// rint(v * 2^24) / rint(w * 2^20): exact product in float64, round-half-even like numpy.rint
+__device__ __forceinline__ unsigned long long fixed_xyz(float v) {
+  return (unsigned long long)__double2ll_rn((double)v * 16777216.0);
+}
+__device__ __forceinline__ unsigned long long fixed_intensity(float w, ApcCtrl* ctrl) {
+  if (fabsf(w) < 1048576.0f) return (unsigned long long)__double2ll_rn((double)w * 1048576.0);
+  atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+  return 0ull;
+}
+
+// One point per thread per round (measured: 2 or 4 points in flight per thread are slower - fewer
+// resident warps to hide the dependent atomic chain).
 __global__ void __launch_bounds__(256)
 k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
                VoxSlot* __restrict__ slots, uint32_t cap_mask, uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t stride = gridDim.x * blockDim.x;
   APC_STAMP(0, 0);
-  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * VOX_ILP) {
-    float4 p[VOX_ILP];
-    uint64_t key[VOX_ILP];
-    uint32_t slot[VOX_ILP];
-    unsigned long long old[VOX_ILP];
-    bool ok[VOX_ILP];
-#pragma unroll
-    for (int u = 0; u < VOX_ILP; ++u) {
-      const uint32_t i = i0 + u * stride;
-      ok[u] = i < n;
-      if (ok[u]) {
-        p[u] = pts[i];
-        ok[u] = voxel_key(p[u], vs, key[u]);
-        if (!ok[u]) {
-          atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
-          p2slot[i] = VOX_NOSLOT;
-        }
-      }
-      slot[u] = ok[u] ? ((uint32_t)mix64(key[u]) & cap_mask) : 0u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float4 p = pts[i];
+    uint64_t key;
+    if (!voxel_key(p, vs, key)) {
+      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+      p2slot[i] = VOX_NOSLOT;
+      continue;
     }
-#pragma unroll
-    for (int u = 0; u < VOX_ILP; ++u)  // independent first probes, all in flight together
-      if (ok[u]) old[u] = atomicCAS(&slots[slot[u]].key, VOX_EMPTY, (unsigned long long)key[u]);
-#pragma unroll
-    for (int u = 0; u < VOX_ILP; ++u) {
-      if (!ok[u]) continue;
-      const uint32_t i = i0 + u * stride;
-      bool found = (old[u] == VOX_EMPTY || old[u] == key[u]);
-      for (uint32_t probe = 1; !found && probe <= cap_mask; ++probe) {  // rare: linear probing
-        slot[u] = (slot[u] + 1) & cap_mask;
-        const unsigned long long o = atomicCAS(&slots[slot[u]].key, VOX_EMPTY, (unsigned long long)key[u]);
-        found = (o == VOX_EMPTY || o == key[u]);
-      }
-      if (!found) {
-        atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-        p2slot[i] = VOX_NOSLOT;
-        continue;
-      }
-      VoxSlot* s = &slots[slot[u]];
-      p2slot[i] = slot[u];
+    uint32_t slot = (uint32_t)mix64(key) & cap_mask;
+    unsigned long long old = atomicCAS(&slots[slot].key, VOX_EMPTY, (unsigned long long)key);
+    for (uint32_t probe = 1; old != VOX_EMPTY && old != key && probe <= cap_mask; ++probe) {  // linear probing
+      slot = (slot + 1) & cap_mask;
+      old = atomicCAS(&slots[slot].key, VOX_EMPTY, (unsigned long long)key);
+    }
+    VoxSlot* s = &slots[slot];
+    if (old == VOX_EMPTY) {          // owner: nothing to accumulate yet
+      s->owner = i;
+      p2slot[i] = slot;
+    } else if (old == key) {         // joins an existing voxel
+      p2slot[i] = slot;
       atomicMin(&s->first, i);
       atomicAdd(&s->cnt, 1u);
-      // rint(x * 2^24): exact product in float64, round-half-even like numpy.rint
-      atomicAdd(&s->acc[0], (unsigned long long)__double2ll_rn((double)p[u].x * 16777216.0));
-      atomicAdd(&s->acc[1], (unsigned long long)__double2ll_rn((double)p[u].y * 16777216.0));
-      atomicAdd(&s->acc[2], (unsigned long long)__double2ll_rn((double)p[u].z * 16777216.0));
-      long long qi = 0;
-      if (fabsf(p[u].w) < 1048576.0f) qi = __double2ll_rn((double)p[u].w * 1048576.0);
-      else atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
-      atomicAdd(&s->acc[3], (unsigned long long)qi);
+      atomicAdd(&s->acc[0], fixed_xyz(p.x));
+      atomicAdd(&s->acc[1], fixed_xyz(p.y));
+      atomicAdd(&s->acc[2], fixed_xyz(p.z));
+      atomicAdd(&s->acc[3], fixed_intensity(p.w, ctrl));
+    } else {
+      atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+      p2slot[i] = VOX_NOSLOT;
     }
   }
   APC_STAMP(0, 1);
@@ -97,26 +85,55 @@ __device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, 
   return __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sum), cnt), inv_scale));
 }
 
+// A point is its voxel's FIRST when it holds the lowest index of the voxel (owner or joiner); the
+// order-preserving scan over the first-flags numbers the voxels in first-occurrence order.  The
+// centroid (owner's coordinates + the joiners' sums, exact integers, one float64 divide) is
+// computed BEFORE the cross-tile scan so that the slot and owner loads overlap the scan's wait;
+// after the scan only stores remain.
 __global__ void __launch_bounds__(APC_TILE_THREADS)
-k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
+k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
                  VoxSlot* __restrict__ slots, uint32_t* __restrict__ rank_of_slot,
                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
-                 uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles) {
+                 uint64_t* scan_state, ApcCtrl* ctrl, uint32_t n_tiles) {
   __shared__ uint32_t sm_scan[34];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
   const uint32_t tile = blockIdx.x;
   bool is_first[APC_TILE_ITEMS];
   uint32_t slot[APC_TILE_ITEMS];
+  uint4 head[APC_TILE_ITEMS];
   APC_STAMP(1, 0);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
-    is_first[j] = false;
-    slot[j] = VOX_NOSLOT;
-    if (i < n) {
-      slot[j] = p2slot[i];
-      if (slot[j] != VOX_NOSLOT) is_first[j] = (slots[slot[j]].first == i);
+    slot[j] = i < n ? p2slot[i] : VOX_NOSLOT;
+  }
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j)   // {key lo, key hi, first, cnt}: all four loads in flight
+    head[j] = slot[j] != VOX_NOSLOT ? *reinterpret_cast<const uint4*>(&slots[slot[j]]) : make_uint4(0u, 0u, 0u, 0u);
+  uint32_t owner[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) owner[j] = slot[j] != VOX_NOSLOT ? slots[slot[j]].owner : 0u;
+  float4 cen[APC_TILE_ITEMS];
+  uint32_t npts[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    // a slot whose key already reads empty was finalised (and cleaned) by an earlier tile: this
+    // point is then certainly not the first of its voxel
+    is_first[j] = slot[j] != VOX_NOSLOT && !(head[j].x == 0xffffffffu && head[j].y == 0xffffffffu) &&
+                  i == min(head[j].z, owner[j]);
+    if (is_first[j]) {
+      const float4 po = pts[owner[j]];   // mostly i itself: 3 voxels in 4 hold one point
+      const uint4* raw = reinterpret_cast<const uint4*>(&slots[slot[j]]);
+      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
+      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
+      npts[j] = head[j].w + 1u;
+      const double dc = (double)npts[j];
+      cen[j] = make_float4(fixed_mean(a01.x + fixed_xyz(po.x), dc, 1.0 / 16777216.0),
+                           fixed_mean(a01.y + fixed_xyz(po.y), dc, 1.0 / 16777216.0),
+                           fixed_mean(a23.x + fixed_xyz(po.z), dc, 1.0 / 16777216.0),
+                           fixed_mean(a23.y + fixed_intensity(po.w, ctrl), dc, 1.0 / 1048576.0));
     }
   }
   uint32_t rank[APC_TILE_ITEMS];
@@ -128,18 +145,11 @@ k_voxel_finalize(uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restri
     if (is_first[j]) {
       const uint32_t s = slot[j];
       const uint32_t r = base + rank[j];
-      // the slot is two 16-byte + one 32-byte aligned pieces of one 64-byte half line
-      uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
-      const uint4 head = raw[0];                                    // key lo/hi, first, cnt
-      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
-      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
-      const uint32_t c = head.w;
-      const double dc = (double)c;
-      out[r] = make_float4(fixed_mean(a01.x, dc, 1.0 / 16777216.0), fixed_mean(a01.y, dc, 1.0 / 16777216.0),
-                           fixed_mean(a23.x, dc, 1.0 / 16777216.0), fixed_mean(a23.y, dc, 1.0 / 1048576.0));
-      if (out_counts) out_counts[r] = c;
+      out[r] = cen[j];
+      if (out_counts) out_counts[r] = npts[j];
       rank_of_slot[s] = r;
       // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0, acc = 0}
+      uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
       raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
       raw[1] = make_uint4(0u, 0u, 0u, 0u);
       raw[2] = make_uint4(0u, 0u, 0u, 0u);
@@ -188,14 +198,14 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
   {
     APC_PROF(ctx, "k_voxel_insert", s);
-    const uint32_t ib = min(apc_div_up(n_max, 256 * VOX_ILP), (uint32_t)APC_SM_COUNT * 8);
+    const uint32_t ib = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
     k_voxel_insert<<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
                                       ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
   }
   APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_PROF(ctx, "k_voxel_finalize", s);
-  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
+  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
                                                         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts,
                                                         out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
   APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
