@@ -18,7 +18,7 @@ APC_MAX_TRANSFORMS = 3
 
 APC_OK, APC_ERR_CUDA, APC_ERR_BAD_ARG, APC_ERR_KEY_RANGE, APC_ERR_CAPACITY, APC_ERR_TOO_FEW = 0, -1, -2, -3, -4, -5
 CROP_NUMPY, CROP_TORCH, CROP_OPEN3D = 0, 1, 2
-DEDUP_OFF, DEDUP_OPEN3D = 0, 1
+DEDUP_OFF, DEDUP_OPEN3D, DEDUP_NUMPY, DEDUP_TORCH_COMPAT = 0, 1, 2, 3
 STAGE_NANSKIP, STAGE_DEDUP, STAGE_FINITE, STAGE_CROP = 1, 2, 4, 8
 (CNT_INPUT, CNT_FILTERED, CNT_VOXELS, CNT_AFTER_STAT, CNT_AFTER_RADIUS, CNT_GROUND_INLIERS, CNT_OUTPUT,
  CNT_STATUS) = range(8)
@@ -76,6 +76,7 @@ def _load():
         "apc_crop_mask": [vp, vp, u32, vp, C.POINTER(f64), C.POINTER(f64), i32, i32, vp, vp],
         "apc_non_finite_mask": [vp, vp, u32, vp, i32, i32, vp, vp],
         "apc_duplicate_mask": [vp, vp, u32, vp, vp, vp],
+        "apc_unique_rows": [vp, vp, u32, vp, vp, vp, vp, vp],
         "apc_select_by_mask": [vp, vp, u32, vp, vp, i32, vp, vp, vp, vp],
         "apc_gather": [vp, vp, u32, vp, u32, vp, vp, vp],
         "apc_pack_xyzi": [vp, vp, vp, u32, vp, vp],
@@ -112,7 +113,7 @@ lib = _load()
 #: every symbol include/apc.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "apc_version",
            "apc_ctx_max_points", "apc_frontend", "apc_unpack", "apc_transform", "apc_crop_mask",
-           "apc_non_finite_mask", "apc_duplicate_mask", "apc_select_by_mask", "apc_gather",
+           "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
            "apc_statistical_outliers", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run",
            "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",

@@ -80,6 +80,12 @@ struct apc_ctx {
   uint8_t* mask_a = nullptr;
   uint32_t* idx_a = nullptr;
   uint32_t* dev_counts = nullptr;   // [16] intermediate device counters
+  // sorted-unique rows (sort.cu), allocated on first use
+  uint4* sort_a = nullptr;          // [max_points] {kx, ky, kz, index} ping
+  uint4* sort_b = nullptr;          // pong
+  uint32_t* sort_hist = nullptr;    // [12][256] digit histograms
+  uint64_t* sort_status = nullptr;  // [sort tiles][256] look-back words
+  uint32_t* sort_idx = nullptr;     // [max_points] first-index / inverse list of the pipeline's sort modes
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.

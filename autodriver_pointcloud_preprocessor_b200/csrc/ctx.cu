@@ -15,6 +15,7 @@ int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s);
 int apc_dedup_reset(apc_ctx* ctx, cudaStream_t s);
 int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s);
 void apc_neighbors_release(apc_ctx* ctx);
+void apc_sort_release(apc_ctx* ctx);
 
 static int reset_tables(apc_ctx* ctx, cudaStream_t s) {
   int rc = apc_voxel_reset(ctx, s);
@@ -68,6 +69,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   if (!ctx) return APC_OK;
   cudaSetDevice(ctx->device);
   apc_neighbors_release(ctx);
+  apc_sort_release(ctx);
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,

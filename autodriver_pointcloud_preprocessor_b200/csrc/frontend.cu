@@ -229,6 +229,51 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
   APC_STAMP(1, 3);
 }
 
+// Second half of the front end for the sorted duplicate-removal back ends (numpy / torch,
+// utils.py:520-542): the rows to keep arrive as an index list into the NaN-skipped cloud (sorted
+// first occurrences, or torch's inverse map), so the load is a gather; non-finite filter,
+// transforms, crop and the ordered compaction are the same as in k_frontend.
+__global__ void __launch_bounds__(APC_TILE_THREADS)
+k_frontend_gather(const __grid_constant__ FrontendParams prm, const float4* __restrict__ src,
+                  const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src_orig, uint32_t n_max,
+                  const uint32_t* n_dev) {
+  __shared__ uint32_t sm_scan[34];
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t epoch = prm.ctrl->epoch;
+  const uint32_t tile = blockIdx.x;
+  bool keep[APC_TILE_ITEMS];
+  float4 v[APC_TILE_ITEMS];
+  uint32_t g[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    keep[j] = false;
+    g[j] = 0u;
+    if (i < n) {
+      g[j] = idx[i];
+      const float4 p = src[g[j]];
+      float x = p.x, y = p.y, z = p.z;
+      bool alive = true;
+      if (prm.remove_nan && (is_nan_f(x) || is_nan_f(y) || is_nan_f(z))) alive = false;
+      if (prm.remove_inf && (is_inf_f(x) || is_inf_f(y) || is_inf_f(z))) alive = false;
+      for (uint32_t k = 0; k < prm.n_T; ++k) xform_f32(prm.T[k], x, y, z);
+      if (prm.crop_enable && alive) alive = crop_keep(prm, x, y, z);
+      v[j] = make_float4(x, y, z, p.w);
+      keep[j] = alive;
+    }
+  }
+  uint32_t rank[APC_TILE_ITEMS];
+  const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, prm.scan_state, tile, epoch, prm.out_count, prm.n_tiles);
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    if (keep[j]) {
+      const uint32_t o = base + rank[j];
+      prm.out_xyzi[o] = v[j];
+      if (prm.out_src) prm.out_src[o] = src_orig ? src_orig[g[j]] : g[j];
+    }
+  }
+}
+
 // ---- generic fill (hash-table clears) -----------------------------------------------------
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -326,7 +371,7 @@ static int build_params(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   if (cfg) {
     APC_REQUIRE(ctx, cfg->n_transforms <= APC_MAX_TRANSFORMS, "too many transforms");
     APC_REQUIRE(ctx, cfg->crop_mode >= 0 && cfg->crop_mode <= 2, "bad crop mode");
-    APC_REQUIRE(ctx, cfg->dedup_mode == APC_DEDUP_OFF || cfg->dedup_mode == APC_DEDUP_OPEN3D, "bad dedup mode");
+    APC_REQUIRE(ctx, cfg->dedup_mode >= APC_DEDUP_OFF && cfg->dedup_mode <= APC_DEDUP_TORCH_COMPAT, "bad dedup mode");
     prm.skip_nans = cfg->skip_nans != 0;
     prm.dedup = cfg->dedup_mode == APC_DEDUP_OPEN3D;
     prm.remove_nan = cfg->remove_nan != 0;
@@ -363,11 +408,68 @@ static int set_smem(apc_ctx* ctx, uint32_t smem) {
   return APC_OK;
 }
 
+int apc_unique_rows_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, int,
+                            cudaStream_t);
+int apc_sort_prepare(apc_ctx*);
+int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                         const apc_filter_cfg* cfg, float* out_xyzi, uint32_t* out_src_idx,
+                         uint8_t* out_stage_mask, uint32_t* out_count_dev, int scan_slot, cudaStream_t s);
+
+// Front end with the numpy / torch duplicate-removal back ends: those return the rows in sorted
+// order (utils.py:532-542), so the chain is NaN skip (k_frontend, everything else off) ->
+// sorted unique rows (sort.cu) -> gather + remaining filters (k_frontend_gather).
+static int frontend_sorted_dedup(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                 const apc_filter_cfg* cfg, float* out_xyzi, uint32_t* out_src_idx,
+                                 uint8_t* out_stage_mask, uint32_t* out_count_dev, int scan_slot, cudaStream_t s) {
+  APC_REQUIRE(ctx, !out_stage_mask, "per-point stage masks are not defined for the sorted duplicate-removal back ends");
+  APC_REQUIRE(ctx, ctx->sort_a, "sort scratch not prepared");
+  uint32_t n_total = 0;
+  for (uint32_t i = 0; i < n_clouds && i < APC_MAX_CLOUDS; ++i) {
+    APC_REQUIRE(ctx, !clouds[i].has_transform, "per-sensor transforms cannot be combined with the sorted duplicate-removal back ends");
+    n_total += clouds[i].n_points;
+  }
+  apc_filter_cfg first;
+  memset(&first, 0, sizeof(first));
+  first.skip_nans = cfg->skip_nans;
+  uint32_t* dc = ctx->dev_counts;
+  float* stage_xyzi = reinterpret_cast<float*>(ctx->sorted_pts);
+  int rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &first, stage_xyzi, out_src_idx ? ctx->idx_a : nullptr, nullptr,
+                                dc + 14, scan_slot, s);
+  if (rc) return rc;
+  if (n_total == 0) {
+    APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
+    return APC_OK;
+  }
+  const bool numpy_mode = cfg->dedup_mode == APC_DEDUP_NUMPY;
+  rc = apc_unique_rows_nobegin(ctx, stage_xyzi, n_total, dc + 14, numpy_mode ? ctx->sort_idx : nullptr,
+                               numpy_mode ? nullptr : ctx->sort_idx, dc + 13, 5, s);
+  if (rc) return rc;
+  FrontendParams prm;
+  uint32_t total = 0, smem = 0;
+  rc = build_params(ctx, clouds, n_clouds, cfg, prm, &total, &smem);
+  if (rc) return rc;
+  prm.out_xyzi = reinterpret_cast<float4*>(out_xyzi);
+  prm.out_src = out_src_idx;
+  prm.out_count = out_count_dev;
+  prm.scan_state = ctx->scan_state[6];
+  prm.n_tiles = apc_div_up(n_total, APC_TILE_POINTS);
+  APC_PROF(ctx, "k_frontend_gather", s);
+  // numpy: one row per unique group; torch as written in the reference: one row per input row
+  k_frontend_gather<<<prm.n_tiles, APC_TILE_THREADS, 0, s>>>(prm, ctx->sorted_pts, ctx->sort_idx,
+                                                             out_src_idx ? ctx->idx_a : nullptr, n_total,
+                                                             numpy_mode ? dc + 13 : dc + 14);
+  APC_LAUNCH_CHECK(ctx, "k_frontend_gather");
+  return APC_OK;
+}
+
 // Internal: front end without the epoch bump (the pipeline bumps once per run).
 int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
                          const apc_filter_cfg* cfg, float* out_xyzi, uint32_t* out_src_idx,
                          uint8_t* out_stage_mask, uint32_t* out_count_dev, int scan_slot, cudaStream_t s) {
   APC_REQUIRE(ctx, out_xyzi && out_count_dev, "output pointer is NULL");
+  if (cfg && (cfg->dedup_mode == APC_DEDUP_NUMPY || cfg->dedup_mode == APC_DEDUP_TORCH_COMPAT))
+    return frontend_sorted_dedup(ctx, clouds, n_clouds, cfg, out_xyzi, out_src_idx, out_stage_mask, out_count_dev,
+                                 scan_slot, s);
   FrontendParams prm;
   uint32_t total = 0, smem = 0;
   int rc = build_params(ctx, clouds, n_clouds, cfg, prm, &total, &smem);
@@ -407,7 +509,9 @@ extern "C" int apc_frontend(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t
                             uint8_t* out_stage_mask, uint32_t* out_count_dev, void* stream) {
   if (!ctx) return APC_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = apc_begin(ctx, s);
+  int rc = APC_OK;
+  if (cfg && cfg->dedup_mode >= APC_DEDUP_NUMPY) rc = apc_sort_prepare(ctx);
+  if (!rc) rc = apc_begin(ctx, s);
   if (rc) return rc;
   return apc_frontend_nobegin(ctx, clouds, n_clouds, cfg, out_xyzi, out_src_idx, out_stage_mask,
                               out_count_dev, 0, s);

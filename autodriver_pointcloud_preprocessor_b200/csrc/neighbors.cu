@@ -38,7 +38,11 @@ struct GridDev {
   uint32_t* rank;            // [levels][n_max] arrival rank of point i inside its cell
   float4* sorted;            // [levels][n_max] xyz + original index (bits in w)
   float* cell;               // [levels] cell sizes (device)
+  float cell0;               // > 0: single-level grid whose cell size the host knows (no k_grid_cells launch)
 };
+__device__ __forceinline__ float grid_cell_size(const GridDev& g, uint32_t level) {
+  return g.cell0 > 0.0f ? g.cell0 : g.cell[level];
+}
 
 __device__ __forceinline__ bool grid_coord(float x, float y, float z, float c, int32_t& ix, int32_t& iy, int32_t& iz) {
   const float qx = floorf(__fdiv_rn(x, c)), qy = floorf(__fdiv_rn(y, c)), qz = floorf(__fdiv_rn(z, c));
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256)
 k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
-  const float c = g.cell[level];
+  const float c = grid_cell_size(g, level);
   APC_STAMP(1, 0);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(128)
 k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
                uint8_t* __restrict__ mask, uint32_t* __restrict__ counts) {
   const uint32_t n = apc_count(n_dev, n_max);
-  const float c = g.cell[0];
+  const float c = grid_cell_size(g, 0);
   APC_STAMP(0, 0);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const float4 q = g.sorted[j];
@@ -493,7 +497,8 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
     k_bbox_init<<<1, 32, 0, s>>>(ctx->ctrl);
     k_bbox<<<bx, 256, 0, s>>>(pts, n_max, n_dev, ctx->ctrl);
   }
-  k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
+  g.d.cell0 = (g.d.levels == 1 && cell_hint > 0.0f) ? cell_hint : 0.0f;
+  if (!(g.d.cell0 > 0.0f)) k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
   const dim3 grid(bx, g.d.levels);
   {
     APC_PROF(ctx, "k_grid_insert", s);
@@ -536,6 +541,73 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   APC_PROF(ctx, "k_grid_clean", s);
   k_grid_clean<<<grid, 256, 0, s>>>(n_max, n_dev, g.d);
   APC_LAUNCH_CHECK(ctx, "radius_outliers");
+  return APC_OK;
+}
+
+// select_by_mask over the radius decision + grid clean-up in one launch (both walk the points in
+// original order): keeps the points whose mask is set, in order, and the points that own rank 0
+// of their cell reset the cell's slot for the next frame.
+__global__ void __launch_bounds__(APC_TILE_THREADS)
+k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev, const uint8_t* __restrict__ mask,
+                GridDev g, float4* __restrict__ out, uint32_t* out_count, uint64_t* scan_state, const ApcCtrl* ctrl,
+                uint32_t n_tiles) {
+  __shared__ uint32_t sm_scan[34];
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t epoch = ctrl->epoch;
+  const uint32_t tile = blockIdx.x;
+  bool keep[APC_TILE_ITEMS];
+  float4 v[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    keep[j] = false;
+    if (i < n) {
+      keep[j] = mask[i] != 0;
+      v[j] = in[i];
+      const uint32_t slot = g.slot[i];
+      if (slot != GRID_NOSLOT && g.rank[i] == 0) {
+        g.keys[slot] = GRID_EMPTY;
+        g.fill[slot] = 0u;
+      }
+    }
+  }
+  uint32_t rank[APC_TILE_ITEMS];
+  const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j)
+    if (keep[j]) out[base + rank[j]] = v[j];
+}
+
+// radius outlier removal + select_by_mask for the pipeline: query, then the fused select/clean
+int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_points,
+                              double radius, uint8_t* mask_scratch, float* out_xyzi, uint32_t* out_count_dev,
+                              int scan_slot, cudaStream_t s) {
+  APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
+  if (n_max == 0) {
+    APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
+    return APC_OK;
+  }
+  APC_REQUIRE(ctx, xyzi && mask_scratch && out_xyzi, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  APC_REQUIRE(ctx, nb_points >= 1 && radius > 0.0, "nb_points must be >= 1 and radius > 0");
+  int rc = apc_neighbors_prepare(ctx, 0);
+  if (rc) return rc;
+  GridHost& g = scratch_of(ctx)->grid[0];
+  const float r32 = (float)radius;
+  const float4* pts = reinterpret_cast<const float4*>(xyzi);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s);
+  if (rc) return rc;
+  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  {
+    APC_PROF(ctx, "k_radius_query", s);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)nb_points, 0, mask_scratch, nullptr);
+  }
+  const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
+  APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
+  APC_PROF(ctx, "k_radius_select", s);
+  k_radius_select<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, mask_scratch, g.d, reinterpret_cast<float4*>(out_xyzi),
+                                                       out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
+  APC_LAUNCH_CHECK(ctx, "radius_select");
   return APC_OK;
 }
 

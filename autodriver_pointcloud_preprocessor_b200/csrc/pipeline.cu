@@ -12,12 +12,14 @@ int apc_voxel_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, float, 
                       int, cudaStream_t);
 int apc_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, const uint8_t*, int, float*, uint32_t*,
                        uint32_t*, int, cudaStream_t);
-int apc_radius_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, uint32_t*, cudaStream_t);
+int apc_radius_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, float*, uint32_t*, int,
+                              cudaStream_t);
 int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
                               const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t);
 int apc_neighbors_prepare(apc_ctx*, int);
+int apc_sort_prepare(apc_ctx*);
 
 // dev_counts layout inside the context
 enum { DC_FILTERED = 1, DC_VOXELS = 2, DC_STAT = 3, DC_RADIUS = 4, DC_OUT = 6, DC_INFO = 8 /* 4 words */ };
@@ -82,10 +84,9 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   }
   if (has_rad) {
     float* out = dst();
-    rc = apc_radius_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
-                            ctx->mask_a, nullptr, s);
-    if (rc) return rc;
-    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, nullptr, dc + DC_RADIUS, 3, s);
+    // the select_by_mask of the radius decision also cleans the neighbour grid (one launch)
+    rc = apc_radius_select_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
+                                   ctx->mask_a, out, dc + DC_RADIUS, 3, s);
     if (rc) return rc;
     cur = out;
     cur_cnt = DC_RADIUS;
@@ -111,6 +112,7 @@ static int prepare(apc_ctx* ctx, const apc_pipeline_cfg* cfg) {
   int rc = APC_OK;
   if (cfg->radius_enable) rc = apc_neighbors_prepare(ctx, 0);
   if (!rc && cfg->stat_enable) rc = apc_neighbors_prepare(ctx, 1);
+  if (!rc && cfg->filter.dedup_mode >= APC_DEDUP_NUMPY) rc = apc_sort_prepare(ctx);
   return rc;
 }
 

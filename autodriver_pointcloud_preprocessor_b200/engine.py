@@ -196,6 +196,18 @@ class Context:
         self._ok(lib.apc_duplicate_mask(self.h, _ptr(xyzi), xyzi.shape[0], None, _ptr(mask), _stream()))
         return mask
 
+    def unique_rows(self, xyzi, want_first=True, want_inverse=False, n_dev=None):
+        """``np.unique(positions, axis=0, return_index=True, return_inverse=True)`` on the device.
+        Returns ``(first_idx int32[n] | None, inverse int32[n] | None, count[1])``; the first
+        ``int(count)`` entries of ``first_idx`` are valid."""
+        n = xyzi.shape[0]
+        first = self._empty((max(n, 1),), torch.int32) if want_first else None
+        inverse = self._empty((max(n, 1),), torch.int32) if want_inverse else None
+        cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._ok(lib.apc_unique_rows(self.h, _ptr(xyzi), n, _ptr(n_dev), _ptr(first), _ptr(inverse), _ptr(cnt),
+                                     _stream()))
+        return first, inverse, cnt
+
     def select_by_mask(self, xyzi, mask, invert=False, want_idx=True):
         """Order-preserving compaction.  Returns ``(xyzi_out, idx, count)`` with full-size
         buffers; slice with ``int(count)``."""

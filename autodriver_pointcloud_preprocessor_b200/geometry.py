@@ -316,6 +316,18 @@ class PointCloud:
         mask = self._ctx().duplicate_mask(self._xyzi())
         return self.select_by_mask(Tensor(mask)), self._home(mask.to(torch.bool))
 
+    def unique_rows_index(self) -> "Tensor":                                        # utils.py:532-533
+        """``np.unique(positions, axis=0, return_index=True)[1]``: lowest input index of every
+        unique row, in lexicographic row order (device sort)."""
+        first, _, cnt = self._ctx().unique_rows(self._xyzi(), want_first=True, want_inverse=False)
+        return Tensor(first[:int(cnt.item())])
+
+    def unique_rows_inverse(self) -> "Tensor":                                      # utils.py:538-540
+        """``torch.unique(positions, dim=0, return_inverse=True)[1]``: unique-row number of every
+        input row (NaN-free input; NaN rows are ordered like numpy orders them)."""
+        _, inverse, _ = self._ctx().unique_rows(self._xyzi(), want_first=False, want_inverse=True)
+        return Tensor(inverse[:self._n()])
+
     def transform(self, T):                                                         # pp.py:482,487,490
         T = T.t.cpu().numpy() if isinstance(T, Tensor) else np.asarray(T)
         ctx = self._ctx()

@@ -15,9 +15,10 @@ Additive parameters (the reference only has a TODO for radius outlier removal, `
 ``remove_radius_outliers`` (False), ``.nb_points`` (5), ``.search_radius`` (0.5),
 ``remove_ground.seed`` (0), ``fused_pipeline`` ('auto').
 
-Deliberate deviations, all visible: ``cpu_backend='torch'`` / ``'numpy'`` duplicate removal
-maps to the Open3D semantics (the torch branch of the reference returns ``points[inverse]``,
-``utils.py:538-542``); normal estimation (``estimate_normals``, default True in the reference)
+Duplicate removal follows the back end the reference would pick (``pp.py:452-460``): numpy ->
+sorted unique rows, torch -> ``points[inverse]`` exactly as ``utils.py:538-542`` is written
+(N rows), anything else -> Open3D semantics; all three run on the device.
+Deliberate deviations, all visible: normal estimation (``estimate_normals``, default True in the reference)
 is not implemented on the GPU yet and is skipped with a warning; visualisation / PCD saving
 need Open3D and are skipped with a warning.
 """
@@ -280,6 +281,13 @@ class PointcloudPreprocessorNode(Node):
             return self.gpu_backend
         return 'open3d'
 
+    def _dedup_mode(self):
+        """C-ABI duplicate-removal mode for the back end string of pp.py:452-460."""
+        if not self.remove_duplicates:
+            return _capi.DEDUP_OFF
+        return {'np': _capi.DEDUP_NUMPY, 'numpy': _capi.DEDUP_NUMPY, 'torch': _capi.DEDUP_TORCH_COMPAT,
+                'pytorch': _capi.DEDUP_TORCH_COMPAT}.get(self._backend().lower(), _capi.DEDUP_OPEN3D)
+
     def _use_fused(self):
         if self.fused_pipeline is True or str(self.fused_pipeline).lower() in ('true', '1', 'on'):
             return True
@@ -390,7 +398,7 @@ class PointcloudPreprocessorNode(Node):
                     'pytorch': _capi.CROP_TORCH}.get(self._backend().lower(), _capi.CROP_OPEN3D)
             crop = dict(min=self.roi_min, max=self.roi_max, invert=self.crop_to_roi_invert, mode=mode)
         fcfg = engine.make_filter_cfg(skip_nans=bool(self.remove_nans and not msg.is_dense),
-                                      dedup_mode=_capi.DEDUP_OPEN3D if self.remove_duplicates else _capi.DEDUP_OFF,
+                                      dedup_mode=self._dedup_mode(),
                                       remove_nan=self.remove_nans, remove_inf=self.remove_infs,
                                       transforms=self._transforms(), crop=crop)
         pcfg = engine.make_pipeline_cfg(
@@ -420,14 +428,10 @@ class PointcloudPreprocessorNode(Node):
         return self.o3d_pointcloud
 
     def _preprocess_staged(self):
-        # Remove duplicate points (pp.py:450-463).  numpy / torch back ends map to Open3D semantics.
+        # Remove duplicate points (pp.py:450-463), with the back end the reference would use.
         if self.remove_duplicates:
             start_time = get_current_time(monotonic=True)
             backend = self._backend()
-            if backend.lower() in ('np', 'numpy', 'torch', 'pytorch'):
-                self._warn_once(f"remove_duplicates backend '{backend}' is mapped to the Open3D semantics "
-                                "(bit-pattern keys, first occurrence kept, order preserved)")
-                backend = 'open3d'
             self.o3d_pointcloud, dupl_msg = remove_duplicates(self.o3d_pointcloud, backend)
             self.processing_times['remove_duplicate_points'] = get_time_difference(start_time, get_current_time(monotonic=True))
 

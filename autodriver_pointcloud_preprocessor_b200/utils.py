@@ -338,24 +338,26 @@ def structured_numpy_array_to_open3d_tensor_pointcloud(structured_numpy_array):
 
 
 def remove_duplicates(pointcloud, backend='torch'):
-    """utils.py:509-546.
+    """utils.py:509-546, every back end on the device.
 
-    * any backend other than numpy / torch -> ``remove_duplicated_points()``: bit-pattern keys,
-      lowest index kept, order preserved (GPU hash, 128-bit CAS).
-    * ``'np'`` / ``'numpy'`` -> the reference returns the *lexicographically sorted* unique rows
-      (``np.unique(axis=0)``), which needs a multi-key device sort; not implemented yet - raises.
+    * ``'np'`` / ``'numpy'`` -> ``np.unique(points, axis=0, return_index=True)`` then
+      ``select_by_index(first_index)`` (utils.py:532-534): the *lexicographically sorted* unique
+      rows, each represented by its lowest input index; -0.0 == +0.0 merge, NaN rows never do.
+      Here a stable 96-bit-key radix sort + head flags (``apc_unique_rows``).
     * ``'torch'`` / ``'pytorch'`` -> the reference passes ``torch.unique``'s *inverse* map to
-      ``select_by_index`` (utils.py:538-542), returning N rows ``points[inverse]``; that defect is
-      not reproduced - raises.  The node therefore maps its default ``cpu_backend='torch'`` to
-      the Open3D semantics (see ``pointcloud_preprocessor.py``).
+      ``select_by_index`` (utils.py:538-542), so the result has N rows ``points[inverse]``.
+      Reproduced as written (same sort, inverse map); identical to torch on NaN-free input, which
+      is what reaches this stage once read_points has skipped NaN rows.
+    * anything else -> ``remove_duplicated_points()``: bit-pattern keys, lowest index kept, order
+      preserved (GPU hash).
     """
     msg = ''
     if backend.lower() in ['np', 'numpy']:
-        raise NotImplementedError("remove_duplicates(backend='numpy'): sorted-unique output needs a device "
-                                  "multi-key sort (not implemented); use the open3d backend")
+        first_index = pointcloud.unique_rows_index()
+        pointcloud = pointcloud.select_by_index(first_index)
     elif backend.lower() in ['torch', 'pytorch']:
-        raise NotImplementedError("remove_duplicates(backend='torch') returns points[inverse] in the reference "
-                                  "(utils.py:538-542); that defect is not reproduced; use the open3d backend")
+        inverse = pointcloud.unique_rows_inverse()
+        pointcloud = pointcloud.select_by_index(inverse)
     else:
         pointcloud, duplicates_mask = pointcloud.remove_duplicated_points()
         msg = f'{msg} Using Open3D pointcloud.remove_duplicated_points()'

@@ -136,6 +136,7 @@ def algorithmic_bytes(kernel: str, c) -> float | None:
         "k_radius_query": 16 * P + 1 * P,                           # every neighbour read is an on-chip re-read
         "k_grid_clean": 8 * P,
         "k_select_by_mask": 16 * P + 1 * P + 16 * P,
+        "k_radius_select": 16 * P + 1 * P + 8 * P + 16 * float(c["P_ground_in"]),   # points + mask + slot/rank, write survivors
         "k_rs_score": 16 * float(c["P_ground_in"]),                 # one pass over the points for all hypotheses
         "k_rs_final": 16 * float(c["P_ground_in"]) + float(c["P_ground_in"]),
     }

@@ -82,7 +82,9 @@ enum { APC_CROP_NUMPY = 0,  /* float64 compare; invert = any(p<=min | p>=max) */
 
 /* duplicate-removal back ends, utils.py:520,535,543 */
 enum { APC_DEDUP_OFF = 0,
-       APC_DEDUP_OPEN3D = 1 /* bit-pattern key, lowest index kept, order preserved */ };
+       APC_DEDUP_OPEN3D = 1, /* remove_duplicated_points: bit-pattern key, lowest index kept, order preserved */
+       APC_DEDUP_NUMPY = 2,  /* np.unique(axis=0, return_index): sorted unique rows, -0 == +0, NaN rows kept */
+       APC_DEDUP_TORCH_COMPAT = 3 /* utils.py:538-542 as written: points[inverse of torch.unique], N rows */ };
 
 typedef struct apc_filter_cfg {
   int32_t skip_nans;      /* read_points: (skip_nans && !is_dense), utils.py:209 */
@@ -160,6 +162,17 @@ int apc_non_finite_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const u
                         int remove_nan, int remove_inf, uint8_t* out_mask, void* stream);
 int apc_duplicate_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
                        uint8_t* out_mask, void* stream);
+
+/* np.unique(points, axis=0, return_index=True, return_inverse=True) on the positions of an SoA
+ * cloud (utils.py:532-533 numpy back end; torch.unique(dim=0, return_inverse=True),
+ * utils.py:538-540): rows ordered lexicographically x, y, z with float comparison (-0 == +0, NaN
+ * last), a row holding a NaN is never merged.  out_first_idx uint32[n_max]: lowest input index of
+ * every unique row, in sorted row order; out_inverse uint32[n_max]: unique-row number of every
+ * input point; either may be NULL.  out_count_dev uint32[1]: number of unique rows.  A stable
+ * 96-bit-key radix sort (12 passes of 8 bits) on the device. */
+int apc_unique_rows(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                    uint32_t* out_first_idx, uint32_t* out_inverse, uint32_t* out_count_dev,
+                    void* stream);
 
 /* select_by_mask (utils.py:271,297; pp.py:542 with invert): order-preserving compaction.
  * out_idx (uint32[n_max], may be NULL) receives the surviving indices. */

@@ -61,3 +61,30 @@ def torch_compat_index_numpy(pos: np.ndarray) -> np.ndarray:
     what reaches this stage when ``remove_nans`` is set: read_points drops NaN rows first)."""
     _, inverse = np.unique(pos, axis=0, return_inverse=True)
     return np.asarray(inverse).reshape(-1)
+
+
+def sort_keys(pos: np.ndarray) -> np.ndarray:
+    """Order-preserving float32 -> uint32 map the CUDA sort uses (csrc/sort.cu:sort_key_f32),
+    restated: NaN -> 0xffffffff (after +inf, all NaNs tie), +-0 -> 0x80000000, negative values
+    bit-inverted, positive values with the sign bit set."""
+    b = np.ascontiguousarray(pos, dtype=np.float32).view(np.uint32).reshape(-1, 3).copy()
+    mag = b & np.uint32(0x7fffffff)
+    k = np.where((b & np.uint32(0x80000000)) != 0, ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+    k[mag == 0] = 0x80000000
+    k[mag > 0x7f800000] = 0xffffffff
+    return k
+
+
+def unique_rows_model(pos: np.ndarray):
+    """``(first_index, inverse)`` by the algorithm of the CUDA path: stable sort on the 96-bit
+    key, a row starts a new group when its key differs from the previous row's or holds a NaN.
+    ``tests/test_oracle_golden.py`` holds it against ``np.unique`` and the reference goldens, so
+    the key rules are pinned independently of the GPU."""
+    k = sort_keys(pos)
+    order = np.lexsort((k[:, 2], k[:, 1], k[:, 0]))
+    ks = k[order]
+    head = np.ones(k.shape[0], dtype=bool)
+    head[1:] = (ks[1:] != ks[:-1]).any(axis=1) | (ks[1:] == 0xffffffff).any(axis=1)
+    inverse = np.empty(k.shape[0], dtype=np.int64)
+    inverse[order] = np.cumsum(head) - 1
+    return order[head], inverse

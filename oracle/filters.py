@@ -110,3 +110,29 @@ def frontend(pos, *, nanskip_mask=None, dedup_mask_fn=None, remove_nan=True, rem
     stage[alive] |= 8
     src = np.flatnonzero(alive).astype(np.uint32)
     return p[src], src, stage
+
+
+def frontend_sorted(pos, index_fn, *, nanskip_mask=None, remove_nan=True, remove_infinite=True,
+                    transforms=(), crop=None):
+    """The front end with the numpy / torch duplicate-removal back ends (utils.py:520-542), which
+    *reorder* the cloud: ``index_fn(points)`` is ``oracle.dedup.numpy_index`` (sorted first
+    occurrences) or ``torch_compat_index`` (the inverse map, N rows); the rows it selects then go
+    through non-finite -> transform(s) -> crop in that order (pp.py:466-506).
+
+    Returns ``(positions_out, src_idx)``; ``src_idx`` indexes the input rows (with repeats in the
+    torch mode).
+    """
+    n = pos.shape[0]
+    alive = np.ones(n, dtype=bool) if nanskip_mask is None else nanskip_mask
+    idx0 = np.flatnonzero(alive)
+    sel = np.asarray(index_fn(pos[idx0])).reshape(-1).astype(np.int64)
+    order = idx0[sel]
+    p = pos[order].astype(np.float32).copy()
+    keep = np.ones(order.shape[0], dtype=bool)
+    if remove_nan or remove_infinite:
+        keep &= non_finite_mask(p, remove_nan, remove_infinite)
+    for T in transforms:
+        p = transform(p, T)
+    if crop is not None:
+        keep &= crop_mask(p, crop["min"], crop["max"], crop.get("invert", False), crop.get("mode", CROP_OPEN3D))
+    return p[keep], order[keep].astype(np.uint32)

@@ -67,14 +67,21 @@ def preprocess(cloud_msgs, cfg, per_sensor_transforms=None):
         inten = (arr[meta["intensity_field_name"]].astype(np.float32) if meta["has_intensity"]
                  else np.zeros(n, np.float32))
         dd = None
-        if cfg["dedup_mode"] == odedup.DEDUP_OPEN3D:
-            dd = odedup.open3d_mask
-        elif cfg["dedup_mode"] != odedup.DEDUP_OFF:
-            raise NotImplementedError("pipeline oracle covers the open3d dedup mode")
-        p, src, stage = filters.frontend(
-            pos, nanskip_mask=nanskip, dedup_mask_fn=dd, remove_nan=cfg["remove_nans"],
-            remove_infinite=cfg["remove_infs"], transforms=list(sensor_T) + list(cfg["transforms"]),
-            crop=cfg["crop"])
+        if cfg["dedup_mode"] in (odedup.DEDUP_NUMPY, odedup.DEDUP_TORCH_COMPAT):
+            if len(cloud_msgs) != 1 or len(sensor_T):
+                raise NotImplementedError("the sorted dedup modes are defined for one sensor without a per-sensor transform")
+            fn = odedup.numpy_index if cfg["dedup_mode"] == odedup.DEDUP_NUMPY else odedup.torch_compat_index_numpy
+            p, src = filters.frontend_sorted(
+                pos, fn, nanskip_mask=nanskip, remove_nan=cfg["remove_nans"], remove_infinite=cfg["remove_infs"],
+                transforms=list(cfg["transforms"]), crop=cfg["crop"])
+            stage = np.zeros(n, dtype=np.uint8)     # per-point stage bits are not defined once rows are reordered
+        else:
+            if cfg["dedup_mode"] == odedup.DEDUP_OPEN3D:
+                dd = odedup.open3d_mask
+            p, src, stage = filters.frontend(
+                pos, nanskip_mask=nanskip, dedup_mask_fn=dd, remove_nan=cfg["remove_nans"],
+                remove_infinite=cfg["remove_infs"], transforms=list(sensor_T) + list(cfg["transforms"]),
+                crop=cfg["crop"])
         pos_all.append(p)
         int_all.append(inten[src])
         stage_all.append(stage)

@@ -88,11 +88,18 @@ def test_host_helpers_match_reference(golden_dir):
             assert np.array_equal(v, c[f"{name}__{k}"], equal_nan=True) and v.dtype == c[f"{name}__{k}"].dtype
 
 
-def test_dedup_backends_fail_loudly():
-    from autodriver_pointcloud_preprocessor_b200 import utils
-    for backend in ("numpy", "torch"):
-        with pytest.raises(NotImplementedError):
-            utils.remove_duplicates(object(), backend=backend)
+def test_dedup_backends_have_no_cpu_path():
+    """numpy / torch duplicate removal run on the device (sorted unique rows); without a CUDA device
+    they fail loudly instead of falling back to np.unique / torch.unique."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: covered by the gpu tests")
+    from autodriver_pointcloud_preprocessor_b200 import geometry, utils
+    pcd = geometry.PointCloud()
+    pcd.point["positions"] = geometry.Tensor(torch.zeros((4, 3), dtype=torch.float32))
+    for backend in ("numpy", "torch", "open3d"):
+        with pytest.raises((RuntimeError, AssertionError)):
+            utils.remove_duplicates(pcd, backend=backend)
 
 
 def test_sensor_synchronizer():

@@ -52,6 +52,27 @@ def test_dedup_matches_reference(golden_dir):
     assert m[10] and m[20] and m[30] and not m[40]
 
 
+def test_sort_key_model(golden_dir):
+    """The key rules of the CUDA sorted-unique path (csrc/sort.cu), restated in
+    oracle.dedup.unique_rows_model, against the reference golden and np.unique on adversarial rows."""
+    g = np.load(os.path.join(golden_dir, "dedup.npz"))
+    first, inverse = odedup.unique_rows_model(g["points"])
+    assert np.array_equal(first, g["numpy_index"])                       # reference numpy back end
+    finite = np.isfinite(g["points"]).all(axis=1)
+    _, inv_f = odedup.unique_rows_model(g["points"][finite])
+    assert np.array_equal(inv_f, odedup.torch_compat_index(g["points"][finite]))   # reference torch back end
+    rng = np.random.default_rng(5)
+    vals = np.array([0.0, -0.0, np.nan, -np.nan, np.inf, -np.inf, 1.0, -1.0, 1e-45, -1e-45, 3.5, 2.0,
+                     np.float32(3.4e38), np.float32(-3.4e38)], np.float32)
+    for _ in range(100):
+        n = int(rng.integers(1, 300))
+        q = vals[rng.integers(0, len(vals), size=(n, 3))]
+        q.view(np.uint32)[np.isnan(q) & (rng.random(q.shape) < 0.5)] |= np.uint32(0x1234)   # NaN payloads
+        first, inverse = odedup.unique_rows_model(q)
+        _, fi, ii = np.unique(q, axis=0, return_index=True, return_inverse=True)
+        assert np.array_equal(first, fi) and np.array_equal(inverse, np.asarray(ii).reshape(-1))
+
+
 def test_convert_and_metadata_match_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "convert.npz"))
     meta = json.load(open(os.path.join(golden_dir, "metadata.json")))
