@@ -85,6 +85,7 @@ def _load():
         "apc_voxel_mean_attr": [vp, vp, vp, u32, vp, vp, vp, vp],
         "apc_radius_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp],
         "apc_statistical_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp, vp],
+        "apc_estimate_normals": [vp, vp, u32, vp, i32, f64, vp, vp, vp, vp],
         "apc_segment_plane": [vp, vp, u32, vp, f64, i32, i32, f64, C.c_uint64, vp, vp, vp, vp, vp],
         "apc_segment_plane_scores": [vp, vp, u32, vp],
         "apc_repack": [vp, vp, u32, vp, C.POINTER(OutField), u32, u32, vp, vp],
@@ -115,7 +116,7 @@ SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "
            "apc_ctx_max_points", "apc_frontend", "apc_unpack", "apc_transform", "apc_crop_mask",
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
-           "apc_statistical_outliers", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run",
+           "apc_statistical_outliers", "apc_estimate_normals", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run",
            "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",
            "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report", "apc_pack_xyzi",
            "apc_split_xyzi"]

@@ -685,3 +685,223 @@ extern "C" int apc_statistical_outliers(apc_ctx* ctx, const float* xyzi, uint32_
   return apc_statistical_nobegin(ctx, xyzi, n_max, n_dev, nb_neighbors, std_ratio, 0.0f, out_mask, out_avg,
                                  out_stats_dev, s);
 }
+
+// ---- normal estimation (estimate_normals(radius, max_nn), pp.py:521-530) -------------
+// Open3D's tensor EstimateNormals with both arguments set = hybrid search: the max_nn nearest of
+// the points with d2 <= float32(r)^2 (query included), covariance of that neighbourhood, eigenvector
+// of its smallest eigenvalue by the analytic symmetric 3x3 solver (Eberly, "A Robust Eigensolver for
+// 3x3 Symmetric Matrices"), no orientation step; fewer than 3 neighbours -> identity covariance ->
+// (0, 0, 1).  The neighbourhood is chosen with the float32 distance of the outlier stages and the
+// total order (d2, original index); moments are taken about the query point in float64 (no
+// cancellation whatever the coordinates' magnitude).  oracle/normals.py restates the same steps.
+#define NRM_KMAX 64
+
+struct NearList {
+  unsigned long long key[NRM_KMAX];   // d2 bits << 32 | original index: d2 >= 0, so integer order = (d2, index) order
+  uint32_t pos[NRM_KMAX];             // position of the neighbour in the cell-sorted array
+  uint32_t cnt, worst;
+  __device__ __forceinline__ void find_worst(uint32_t k) {
+    worst = 0;
+    for (uint32_t j = 1; j < k; ++j)
+      if (key[j] > key[worst]) worst = j;
+  }
+  __device__ __forceinline__ void push(unsigned long long kk, uint32_t p, uint32_t k) {
+    if (cnt < k) {
+      key[cnt] = kk;
+      pos[cnt] = p;
+      if (++cnt == k) find_worst(k);
+    } else if (kk < key[worst]) {
+      key[worst] = kk;
+      pos[worst] = p;
+      find_worst(k);
+    }
+  }
+};
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// eigenvector of the (well separated) eigenvalue `ev`: the largest cross product of two rows of A - ev I
+__device__ void eig_vector0(const double* A, double ev, double* v) {
+  const double r0[3] = {A[0] - ev, A[1], A[2]}, r1[3] = {A[1], A[4] - ev, A[5]}, r2[3] = {A[2], A[5], A[8] - ev};
+  double c01[3], c02[3], c12[3];
+  cross3(r0, r1, c01);
+  cross3(r0, r2, c02);
+  cross3(r1, r2, c12);
+  const double d0 = dot3(c01, c01), d1 = dot3(c02, c02), d2 = dot3(c12, c12);
+  const double* best = c01;
+  double dmax = d0;
+  if (d1 > dmax) { dmax = d1; best = c02; }
+  if (d2 > dmax) { dmax = d2; best = c12; }
+  const double inv = 1.0 / sqrt(dmax);
+  v[0] = best[0] * inv; v[1] = best[1] * inv; v[2] = best[2] * inv;
+}
+
+// eigenvector of `ev1` inside the plane orthogonal to the known eigenvector w
+__device__ void eig_vector1(const double* A, const double* w, double ev1, double* v) {
+  double U[3], V[3];
+  if (fabs(w[0]) > fabs(w[1])) {
+    const double inv = 1.0 / sqrt(w[0] * w[0] + w[2] * w[2]);
+    U[0] = -w[2] * inv; U[1] = 0.0; U[2] = w[0] * inv;
+  } else {
+    const double inv = 1.0 / sqrt(w[1] * w[1] + w[2] * w[2]);
+    U[0] = 0.0; U[1] = w[2] * inv; U[2] = -w[1] * inv;
+  }
+  cross3(w, U, V);
+  const double AU[3] = {A[0] * U[0] + A[1] * U[1] + A[2] * U[2], A[1] * U[0] + A[4] * U[1] + A[5] * U[2],
+                        A[2] * U[0] + A[5] * U[1] + A[8] * U[2]};
+  const double AV[3] = {A[0] * V[0] + A[1] * V[1] + A[2] * V[2], A[1] * V[0] + A[4] * V[1] + A[5] * V[2],
+                        A[2] * V[0] + A[5] * V[1] + A[8] * V[2]};
+  double m00 = dot3(U, AU) - ev1, m01 = dot3(U, AV), m11 = dot3(V, AV) - ev1;
+  const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+  if (a00 >= a11) {
+    if (fmax(a00, a01) > 0.0) {
+      if (a00 >= a01) { m01 /= m00; m00 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m00; }
+      else { m00 /= m01; m01 = 1.0 / sqrt(1.0 + m00 * m00); m00 *= m01; }
+      for (int k = 0; k < 3; ++k) v[k] = m01 * U[k] - m00 * V[k];
+    } else {
+      for (int k = 0; k < 3; ++k) v[k] = U[k];
+    }
+  } else {
+    if (fmax(a11, a01) > 0.0) {
+      if (a11 >= a01) { m01 /= m11; m11 = 1.0 / sqrt(1.0 + m01 * m01); m01 *= m11; }
+      else { m11 /= m01; m01 = 1.0 / sqrt(1.0 + m11 * m11); m11 *= m01; }
+      for (int k = 0; k < 3; ++k) v[k] = m11 * U[k] - m01 * V[k];
+    } else {
+      for (int k = 0; k < 3; ++k) v[k] = U[k];
+    }
+  }
+}
+
+// normal = eigenvector of the smallest eigenvalue of the symmetric covariance C (row-major 3x3)
+__device__ void normal_from_covariance(const double* C, double* nrm) {
+  double mx = C[0];
+  for (int k = 1; k < 9; ++k) mx = C[k] > mx ? C[k] : mx;
+  if (mx == 0.0) { nrm[0] = nrm[1] = nrm[2] = 0.0; return; }
+  double A[9];
+  for (int k = 0; k < 9; ++k) A[k] = C[k] / mx;
+  const double norm = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+  if (!(norm > 0.0)) {   // diagonal: the axis of the smallest entry
+    nrm[0] = nrm[1] = nrm[2] = 0.0;
+    if (C[0] < C[4] && C[0] < C[8]) nrm[0] = 1.0;
+    else if (C[4] < C[0] && C[4] < C[8]) nrm[1] = 1.0;
+    else nrm[2] = 1.0;
+    return;
+  }
+  const double q = (A[0] + A[4] + A[8]) / 3.0;
+  const double b00 = A[0] - q, b11 = A[4] - q, b22 = A[8] - q;
+  const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2.0) / 6.0);
+  const double c00 = b11 * b22 - A[5] * A[5], c01 = A[1] * b22 - A[5] * A[2], c02 = A[1] * A[5] - b11 * A[2];
+  const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
+  const double half_det = fmin(fmax(det * 0.5, -1.0), 1.0);
+  const double angle = acos(half_det) / 3.0;
+  const double beta2 = cos(angle) * 2.0, beta0 = cos(angle + 2.09439510239319549) * 2.0, beta1 = -(beta0 + beta2);
+  const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+  double v0[3], v1[3], v2[3];
+  if (half_det >= 0.0) {
+    eig_vector0(A, e2, v2);
+    if (e2 < e0 && e2 < e1) { nrm[0] = v2[0]; nrm[1] = v2[1]; nrm[2] = v2[2]; return; }
+    eig_vector1(A, v2, e1, v1);
+    if (e1 < e0 && e1 < e2) { nrm[0] = v1[0]; nrm[1] = v1[1]; nrm[2] = v1[2]; return; }
+    cross3(v1, v2, nrm);
+  } else {
+    eig_vector0(A, e0, v0);
+    if (e0 < e1 && e0 < e2) { nrm[0] = v0[0]; nrm[1] = v0[1]; nrm[2] = v0[2]; return; }
+    eig_vector1(A, v0, e1, v1);
+    if (e1 < e0 && e1 < e2) { nrm[0] = v1[0]; nrm[1] = v1[1]; nrm[2] = v1[2]; return; }
+    cross3(v0, v1, nrm);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t max_nn, float* __restrict__ normals,
+                uint32_t* __restrict__ counts, double* __restrict__ covariances) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const float c = grid_cell_size(g, 0);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float4 q = g.sorted[j];
+    const uint32_t orig = __float_as_uint(q.w);
+    int32_t ix, iy, iz;
+    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+    NearList nl;
+    nl.cnt = 0;
+    nl.worst = 0;
+    for (int c27 = 0; c27 < 27; ++c27) {
+      const int dx = c27 % 3 - 1, dy = (c27 / 3) % 3 - 1, dz = c27 / 9 - 1;
+      const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
+      if (s == GRID_NOSLOT) continue;
+      const uint32_t b = g.start[s], e = b + g.fill[s];
+      for (uint32_t t = b; t < e; ++t) {
+        const float4 p = g.sorted[t];
+        const float d2 = d2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (d2 <= r2)
+          nl.push(((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w), t, max_nn);
+      }
+    }
+    double C[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};   // fewer than 3 neighbours: identity
+    if (nl.cnt >= 3) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, m00 = 0.0, m01 = 0.0, m02 = 0.0, m11 = 0.0, m12 = 0.0, m22 = 0.0;
+      for (uint32_t k = 0; k < nl.cnt; ++k) {
+        const float4 p = g.sorted[nl.pos[k]];
+        const double x = (double)p.x - (double)q.x, y = (double)p.y - (double)q.y, z = (double)p.z - (double)q.z;
+        s0 += x; s1 += y; s2 += z;
+        m00 += x * x; m01 += x * y; m02 += x * z; m11 += y * y; m12 += y * z; m22 += z * z;
+      }
+      const double inv = 1.0 / (double)nl.cnt;
+      s0 *= inv; s1 *= inv; s2 *= inv;
+      C[0] = m00 * inv - s0 * s0;
+      C[1] = C[3] = m01 * inv - s0 * s1;
+      C[2] = C[6] = m02 * inv - s0 * s2;
+      C[4] = m11 * inv - s1 * s1;
+      C[5] = C[7] = m12 * inv - s1 * s2;
+      C[8] = m22 * inv - s2 * s2;
+    }
+    double nrm[3];
+    normal_from_covariance(C, nrm);
+    normals[3 * (size_t)orig + 0] = (float)nrm[0];
+    normals[3 * (size_t)orig + 1] = (float)nrm[1];
+    normals[3 * (size_t)orig + 2] = (float)nrm[2];
+    if (counts) counts[orig] = nl.cnt;
+    if (covariances)
+      for (int k = 0; k < 9; ++k) covariances[9 * (size_t)orig + k] = C[k];
+  }
+}
+
+int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int max_nn, double radius,
+                        float* out_normals, uint32_t* out_counts, double* out_cov, cudaStream_t s) {
+  if (n_max == 0) return APC_OK;
+  APC_REQUIRE(ctx, xyzi && out_normals, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  APC_REQUIRE(ctx, max_nn >= 1 && max_nn <= NRM_KMAX && radius > 0.0, "max_nn must be in 1..64 and radius > 0");
+  int rc = apc_neighbors_prepare(ctx, 0);
+  if (rc) return rc;
+  GridHost& g = scratch_of(ctx)->grid[0];
+  const float r32 = (float)radius;
+  const float4* pts = reinterpret_cast<const float4*>(xyzi);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s);
+  if (rc) return rc;
+  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  {
+    APC_PROF(ctx, "k_normals_query", s);
+    k_normals_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_normals, out_counts, out_cov);
+  }
+  const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
+  APC_PROF(ctx, "k_grid_clean", s);
+  k_grid_clean<<<grid, 256, 0, s>>>(n_max, n_dev, g.d);
+  APC_LAUNCH_CHECK(ctx, "estimate_normals");
+  return APC_OK;
+}
+
+extern "C" int apc_estimate_normals(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int max_nn,
+                                    double radius, float* out_normals, uint32_t* out_neighbor_counts,
+                                    double* out_covariances, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  return apc_normals_nobegin(ctx, xyzi, n_max, n_dev, max_nn, radius, out_normals, out_neighbor_counts, out_covariances, s);
+}

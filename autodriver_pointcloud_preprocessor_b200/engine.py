@@ -277,6 +277,16 @@ class Context:
                                               float(std_ratio), _ptr(mask), _ptr(avg), _ptr(stats), _stream()))
         return mask[:n], avg[:n], stats
 
+    def estimate_normals(self, xyzi, max_nn, radius, want_counts=False, want_cov=False, n_dev=None):
+        """Returns ``(normals float32[n,3], counts int32[n] | None, covariances float64[n,3,3] | None)``."""
+        n = xyzi.shape[0]
+        normals = self._empty((max(n, 1), 3), torch.float32)
+        counts = self._empty((max(n, 1),), torch.int32) if want_counts else None
+        cov = self._empty((max(n, 1), 3, 3), torch.float64) if want_cov else None
+        self._ok(lib.apc_estimate_normals(self.h, _ptr(xyzi), n, _ptr(n_dev), int(max_nn), float(radius),
+                                          _ptr(normals), _ptr(counts), _ptr(cov), _stream()))
+        return normals[:n], (counts[:n] if counts is not None else None), (cov[:n] if cov is not None else None)
+
     # ---- ransac ------------------------------------------------------------------------------------
     def segment_plane(self, xyzi, distance_threshold, ransac_n, num_iterations, probability, seed=0,
                       sample_table=None, n_dev=None):

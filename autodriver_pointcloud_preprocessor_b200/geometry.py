@@ -242,8 +242,19 @@ class PointCloud:
     def to_legacy(self):                                  # pp.py:367 (visualiser only)
         raise NotImplementedError("legacy Open3D geometry (visualisation) is outside the CUDA hot path")
 
-    def estimate_normals(self, radius=None, max_nn=30):   # pp.py:523
-        raise NotImplementedError("normal estimation is not part of the CUDA hot path yet (SURVEY.md 8 F1)")
+    def estimate_normals(self, max_nn=30, radius=None):   # pp.py:523
+        """Open3D ``estimate_normals``: hybrid search (``max_nn`` nearest within ``radius``) ->
+        covariance -> eigenvector of the smallest eigenvalue; sets ``point['normals']`` (float32
+        N x 3), not oriented.  Both arguments are required here (the reference passes both,
+        pp.py:523-526); pure-KNN / pure-radius searches are not implemented."""
+        if radius is None or max_nn is None:
+            raise NotImplementedError("estimate_normals needs both radius and max_nn (hybrid search, pp.py:523-526)")
+        if self._n() == 0:
+            self.point["normals"] = self._home(torch.zeros((0, 3), dtype=torch.float32, device="cuda"))
+            return self
+        normals, _, _ = self._ctx().estimate_normals(self._xyzi(), int(max_nn), float(radius))
+        self.point["normals"] = self._home(normals.contiguous())
+        return self
 
     def __repr__(self):
         n = 0 if self.is_empty() else len(self.point["positions"])
@@ -335,7 +346,12 @@ class PointCloud:
         pos, _ = ctx.split_xyzi(xyzi, want_intensity=False)
         self.point["positions"] = self._home(pos)
         if "normals" in self.point:
-            raise NotImplementedError("rotating normals is outside the CUDA hot path yet (SURVEY.md 8 F1)")
+            # Open3D rotates the normals by the upper-left 3x3 block (no translation, no divide)
+            R = np.eye(4, dtype=np.float32)
+            R[:3, :3] = T.astype(np.float32)[:3, :3]
+            nrm = ctx.pack_xyzi(self._gpu(self.point["normals"]).to(torch.float32), None)
+            rot, _ = ctx.split_xyzi(ctx.transform(nrm, R), want_intensity=False)
+            self.point["normals"] = self._home(rot)
         return self
 
     def crop_mask(self, min_bound, max_bound, mode=_capi.CROP_OPEN3D, invert=False) -> Tensor:

@@ -18,9 +18,10 @@ Additive parameters (the reference only has a TODO for radius outlier removal, `
 Duplicate removal follows the back end the reference would pick (``pp.py:452-460``): numpy ->
 sorted unique rows, torch -> ``points[inverse]`` exactly as ``utils.py:538-542`` is written
 (N rows), anything else -> Open3D semantics; all three run on the device.
-Deliberate deviations, all visible: normal estimation (``estimate_normals``, default True in the reference)
-is not implemented on the GPU yet and is skipped with a warning; visualisation / PCD saving
-need Open3D and are skipped with a warning.
+Normal estimation (``estimate_normals``, default True like the reference) runs on the device
+(``apc_estimate_normals``) and adds ``normal_x/y/z`` to the published cloud (pp.py:560-567).
+Deliberate deviations, all visible: visualisation / PCD saving need Open3D and are skipped with
+a warning.
 """
 from __future__ import annotations
 
@@ -379,8 +380,6 @@ class PointcloudPreprocessorNode(Node):
         self.get_camera_to_robot_tf(self.pointcloud_metadata["header"].frame_id,
                                     getattr(self.pointcloud_metadata["header"], 'stamp', None))
         self.processing_times['tf_lookup'] = get_time_difference(start_time, get_current_time(monotonic=True))
-        if self.estimate_normals:
-            self._warn_once("estimate_normals=True: normal estimation is not implemented on the GPU yet; skipped")
         if self._use_fused() and self._raw_msg is not None:
             return self._preprocess_fused()
         return self._preprocess_staged()
@@ -411,7 +410,7 @@ class PointcloudPreprocessorNode(Node):
             ground=dict(distance_threshold=self.remove_ground_distance_threshold,
                         ransac_n=self.remove_ground_ransac_number, num_iterations=self.remove_ground_num_iterations,
                         probability=self.remove_ground_probability, seed=self.remove_ground_seed)
-            if self.remove_ground else None)
+            if (self.remove_ground and not self.estimate_normals) else None)
         out, counts, plane = ctx.pipeline_run([desc], pcfg)
         ctx.check()
         c = counts.cpu().numpy()
@@ -425,7 +424,29 @@ class PointcloudPreprocessorNode(Node):
         self._fused_xyzi = (out[:n_out], cloud)       # prepare_pointcloud repacks straight from this
         self.last_counts = c
         self.last_plane = plane.cpu().numpy()
+        if self.estimate_normals:
+            # normals come before the ground stage (pp.py:521-543) and travel through its selection
+            self._normals_and_ground()
         return self.o3d_pointcloud
+
+    def _normals_and_ground(self):
+        """pp.py:521-543 on the carrier: estimate_normals, then segment_plane + select_by_index."""
+        if self.estimate_normals:
+            start_time = get_current_time(monotonic=True)
+            self.o3d_pointcloud.estimate_normals(radius=self.estimate_normals_search_radius,
+                                                 max_nn=self.estimate_normals_max_neighbors)
+            self.pointcloud_metadata['has_normals'] = True
+            self.processing_times['normal_estimation'] = get_time_difference(start_time, get_current_time(monotonic=True))
+        if self.remove_ground:
+            start_time = get_current_time(monotonic=True)
+            plane_model, inliers = self.o3d_pointcloud.segment_plane(
+                distance_threshold=self.remove_ground_distance_threshold,
+                ransac_n=self.remove_ground_ransac_number,
+                num_iterations=self.remove_ground_num_iterations,
+                probability=self.remove_ground_probability, seed=self.remove_ground_seed)
+            self.o3d_pointcloud = self.o3d_pointcloud.select_by_index(inliers, invert=True)
+            self.last_plane = plane_model.cpu().numpy()
+            self.processing_times['ground_segmentation'] = get_time_difference(start_time, get_current_time(monotonic=True))
 
     def _preprocess_staged(self):
         # Remove duplicate points (pp.py:450-463), with the back end the reference would use.
@@ -472,16 +493,7 @@ class PointcloudPreprocessorNode(Node):
                 nb_points=self.remove_radius_outliers_nb_points,
                 search_radius=self.remove_radius_outliers_search_radius)
 
-        if self.remove_ground:
-            start_time = get_current_time(monotonic=True)
-            plane_model, inliers = self.o3d_pointcloud.segment_plane(
-                distance_threshold=self.remove_ground_distance_threshold,
-                ransac_n=self.remove_ground_ransac_number,
-                num_iterations=self.remove_ground_num_iterations,
-                probability=self.remove_ground_probability, seed=self.remove_ground_seed)
-            self.o3d_pointcloud = self.o3d_pointcloud.select_by_index(inliers, invert=True)
-            self.last_plane = plane_model.cpu().numpy()
-            self.processing_times['ground_segmentation'] = get_time_difference(start_time, get_current_time(monotonic=True))
+        self._normals_and_ground()
         return self.o3d_pointcloud
 
     # ------------------------------------------------------------------------------------------------
@@ -490,6 +502,10 @@ class PointcloudPreprocessorNode(Node):
         orig_field_names = [f.name for f in ros_cloud.fields]
         orig_field_types = [f.datatype for f in ros_cloud.fields]
         self.new_dtype = [(name, FIELD_DTYPE_MAP[datatype]) for name, datatype in zip(orig_field_names, orig_field_types)]
+        if self.estimate_normals:                                                   # pp.py:560-567
+            orig_field_names.extend(['normal_x', 'normal_y', 'normal_z'])
+            orig_field_types.extend([PointField.FLOAT32, PointField.FLOAT32, PointField.FLOAT32])
+            self.new_dtype.extend([(n, FIELD_DTYPE_MAP[PointField.FLOAT32]) for n in ('normal_x', 'normal_y', 'normal_z')])
         self.pointfields, self.point_offset = numpy_struct_to_pointcloud2(
             field_names=orig_field_names, field_datatypes=orig_field_types,
             is_dense=self.remove_nans and self.remove_infs)
@@ -526,6 +542,10 @@ class PointcloudPreprocessorNode(Node):
             c = (gpu(o3d_pointcloud.point['rgb']) * 255).clip(0, 255).to(torch.uint8).to(torch.int32)
             packed = ((c[:, 0] << 16) | (c[:, 1] << 8) | c[:, 2]).view(torch.float32)
             source['rgb'] = (5, packed.contiguous())
+        if (self.estimate_normals or pointcloud_metadata.get('has_normals', False)) and 'normal_x' in dtype.names:
+            nrm = gpu(o3d_pointcloud.point['normals']).to(torch.float32)           # pp.py:620-624
+            for k, name in enumerate(('normal_x', 'normal_y', 'normal_z')):
+                source[name] = (5, nrm[:, k].contiguous())
         out_fields = []
         for f in self.pointfields:
             src, attr = source.get(f.name, (0, None))

@@ -226,6 +226,16 @@ int apc_statistical_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_max,
                              uint8_t* out_mask, float* out_avg, double* out_stats_dev,
                              void* stream);
 
+/* estimate_normals(radius, max_nn) (pp.py:521-530, on by default pp.py:176; Open3D hybrid search):
+ * neighbourhood = the max_nn (<= 64) nearest of the points with d2 <= float32(radius)^2, query
+ * included, ties by lower index; normal = eigenvector of the smallest eigenvalue of the
+ * neighbourhood covariance (analytic symmetric 3x3 solver), not oriented; fewer than 3 neighbours
+ * -> (0, 0, 1).  out_normals float32[3*n_max]; out_neighbor_counts uint32[n_max] and
+ * out_covariances double[9*n_max] (row-major, divided by the count) may be NULL. */
+int apc_estimate_normals(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                         int max_nn, double radius, float* out_normals,
+                         uint32_t* out_neighbor_counts, double* out_covariances, void* stream);
+
 /* ---- (4) RANSAC ground plane --------------------------------------------------------- */
 
 /* segment_plane(distance_threshold, ransac_n, num_iterations, probability) (pp.py:533-543).

@@ -9,14 +9,14 @@ carried along.
 ``preprocess`` follows the stage order of ``pp.py:447-544``:
 dedup -> non-finite -> transform(s) -> crop -> voxel -> statistical outliers ->
 [radius outliers - absent from the reference, placed after the statistical stage] ->
-[normals: out of scope] -> RANSAC ground removal.
+normals -> RANSAC ground removal.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import dedup as odedup
-from . import filters, outliers, pc2, ransac, voxel
+from . import filters, normals, outliers, pc2, ransac, voxel
 
 
 def concat(clouds, transforms):
@@ -42,6 +42,7 @@ def default_config():
         voxel_size=0.01,
         statistical=None,            # dict(nb_neighbors=20, std_ratio=2.0)
         radius=None,                 # dict(nb_points=5, radius=0.5)
+        normals=None,                # dict(radius=0.1, max_nn=30)  (pp.py:521-530; on by default in the node)
         ground=None,                 # dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=0)
     )
 
@@ -109,6 +110,9 @@ def preprocess(cloud_msgs, cfg, per_sensor_transforms=None):
         m = outliers.radius_mask(pos, r["nb_points"], r["radius"])
         out["radius_mask"] = m
         pos, inten = pos[m], inten[m]
+    nrm = None
+    if cfg.get("normals"):
+        nrm, out["normal_counts"], _ = normals.estimate_normals(pos, cfg["normals"]["radius"], cfg["normals"]["max_nn"])
     if cfg.get("ground"):
         g = cfg["ground"]
         plane, inl, info = ransac.segment_plane(pos, g["distance_threshold"], g["ransac_n"],
@@ -117,5 +121,8 @@ def preprocess(cloud_msgs, cfg, per_sensor_transforms=None):
         keep = np.ones(pos.shape[0], dtype=bool)
         keep[inl] = False
         pos, inten = pos[keep], inten[keep]
+        nrm = nrm[keep] if nrm is not None else None
+    if nrm is not None:
+        out["normals"] = nrm
     out["positions"], out["intensity"] = pos, inten
     return out

@@ -190,3 +190,44 @@ def test_concatenate_then_voxel():
     ref = voxel.voxel_down_sample(merged["positions"], 0.1, merged["intensity"], fixed=True)
     assert n == ref["positions"].shape[0]
     assert np.array_equal(xyzi.cpu().numpy()[:, :3].view(np.uint32), ref["positions"].view(np.uint32))
+
+
+@pytest.mark.parametrize("layout,fused,backend", [("xyzi16", "auto", "open3d"), ("xyzirt22", "auto", "numpy"),
+                                                  ("xyzirt22", "true", "torch")])
+def test_node_callback_with_normals_and_reference_backends(layout, fused, backend):
+    """The reference's defaults that the other node tests switch off: estimate_normals=True (adds
+    normal_x/y/z to the published cloud, pp.py:560-567, 620-624) and the numpy / torch duplicate
+    removal back ends (sorted unique rows / points[inverse], utils.py:520-542)."""
+    from oracle import dedup as odedup
+    from oracle import pc2
+    scan, msg = scan_msg(layout, seed=47, n_beams=32, n_az=1024)
+    ground = dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=3)
+    node = make_node({"use_gpu": backend == "open3d", "cpu_backend": backend, "voxel_size": 0.1, "remove_ground": True,
+                      "remove_ground.seed": 3, "estimate_normals.search_radius": 0.5, "robot_frame": "base_link",
+                      "fused_pipeline": fused})
+    assert node.estimate_normals is True                                        # reference default, pp.py:176
+    q = [0.0, 0.0, np.sin(0.02), np.cos(0.02)]
+    node.tf_buffer.set_transform("base_link", "lidar", (1.5, -0.25, 1.8), q)
+    node.callback(msg)
+    assert len(node.pointcloud_pub.messages) == 1, "callback dropped the frame"
+    out = node.pointcloud_pub.messages[0]
+    T = node.camera_to_robot_tf.cpu().numpy()
+    mode = {"open3d": odedup.DEDUP_OPEN3D, "numpy": odedup.DEDUP_NUMPY, "torch": odedup.DEDUP_TORCH_COMPAT}[backend]
+    crop_mode = {"open3d": 2, "numpy": 0, "torch": 1}[backend]
+    ref, cfg = oracle_published(msg, dict(voxel_size=0.1, ground=ground, normals=dict(radius=0.5, max_nn=30),
+                                          dedup_mode=mode,
+                                          crop=dict(min=[-60.0, -60.0, -20.0], max=[60.0, 60.0, 20.0], invert=False,
+                                                    mode=crop_mode)), T)
+    names = [f.name for f in msg.fields] + ["normal_x", "normal_y", "normal_z"]
+    assert [f.name for f in out.fields] == names
+    packed, step = pc2.packed_fields(names, [f.datatype for f in msg.fields] + [7, 7, 7])
+    assert out.point_step == step and [(f.name, f.offset, f.datatype) for f in out.fields] == packed
+    assert out.width == ref["positions"].shape[0]
+    arr = np.frombuffer(out.data, dtype=pc2.dtype_from_fields(out.fields, out.point_step))
+    got = np.stack([arr["x"], arr["y"], arr["z"]], 1)
+    assert np.array_equal(got.view(np.uint32), ref["positions"].view(np.uint32))
+    nrm = np.stack([arr["normal_x"], arr["normal_y"], arr["normal_z"]], 1)
+    assert np.allclose(np.linalg.norm(nrm.astype(np.float64), axis=1), 1.0, atol=1e-5)
+    close = np.abs(nrm - ref["normals"]).max(axis=1) < 1e-5                     # float tolerance: 1e-5 per component
+    assert close.mean() > 0.98                                                  # the rest: near-degenerate neighbourhoods
+    assert "normal_estimation" in node.processing_times
