@@ -49,7 +49,7 @@ def gather_outputs(send: torch.Tensor, counts: torch.Tensor, group=None):
 
 class _Lane:
     __slots__ = ("stream", "ctx", "d_in", "d_out", "d_counts", "d_plane", "h_counts", "h_out", "graph",
-                 "resident_graphs", "pending", "event", "desc")
+                 "resident_graphs", "pending", "event", "copy_event", "desc")
 
 
 class ScanPipeline:
@@ -86,6 +86,7 @@ class ScanPipeline:
             ln.resident_graphs = {}
             ln.pending = None
             ln.event = torch.cuda.Event()
+            ln.copy_event = torch.cuda.Event()
             self.lanes.append(ln)
         torch.cuda.synchronize(self.device)
         #: kernels launched per scan by one graph replay (our own kernels; counted at capture)
@@ -116,30 +117,42 @@ class ScanPipeline:
     # ---- end to end: host bytes in, host points out ----------------------------------------------
     def process_host(self, frames, keep_outputs: bool = True):
         """``frames``: pinned uint8 host tensors (one PointCloud2 ``data`` buffer each).
-        Returns ``(outputs, counts)``: per frame a float32 [n_out, 4] numpy array (x, y, z,
-        intensity) and the 8 pipeline counters.  H2D, kernels and D2H of different frames
-        overlap across lanes."""
+        Returns ``(outputs, counts, d2h_bytes)``: per frame a float32 [n_out, 4] numpy array
+        (x, y, z, intensity) and the 8 pipeline counters.
+
+        Software-pipelined per lane so that the host thread never waits for a copy it has just
+        issued: visiting a lane (1) harvests the payload copy issued two visits ago, (2) reads the
+        counters of the previous frame (its graph has had a whole round of the other lanes to
+        finish) and issues the device->host copy of exactly the surviving rows, (3) issues the
+        next frame's upload + graph + counters read-back.  H2D, kernels and D2H of different
+        frames overlap across lanes."""
         results = [None] * len(frames)
         counts = np.zeros((len(frames), 8), dtype=np.int32)
-        d2h_bytes = 0
+        self._d2h_bytes = 0
         S = len(self.lanes)
-        pend = [None] * S
+        for ln in self.lanes:
+            ln.pending = [None, None]                   # [frame whose graph is in flight, (frame, n) whose payload copy is]
         for f, h_in in enumerate(frames):
             ln = self.lanes[f % S]
-            if pend[f % S] is not None:
-                d2h_bytes += self._drain(ln, pend[f % S], results, counts, keep_outputs)
+            self._harvest(ln, results, keep_outputs)
+            self._issue_payload_copy(ln, counts)
             with torch.cuda.stream(ln.stream):
                 ln.d_in.copy_(h_in, non_blocking=True)
                 ln.ctx.launch_graph(ln.graph)
                 ln.h_counts.copy_(ln.d_counts, non_blocking=True)
                 ln.event.record(ln.stream)
-            pend[f % S] = f
-        for l, ln in enumerate(self.lanes):
-            if pend[l] is not None:
-                d2h_bytes += self._drain(ln, pend[l], results, counts, keep_outputs)
-        return results, counts, d2h_bytes
+            ln.pending[0] = f
+        for ln in self.lanes:
+            self._harvest(ln, results, keep_outputs)
+            self._issue_payload_copy(ln, counts)
+        for ln in self.lanes:
+            self._harvest(ln, results, keep_outputs)
+        return results, counts, self._d2h_bytes
 
-    def _drain(self, ln, f, results, counts, keep_outputs):
+    def _issue_payload_copy(self, ln, counts):
+        f = ln.pending[0]
+        if f is None:
+            return
         ln.event.synchronize()
         counts[f] = ln.h_counts.numpy()
         if counts[f, _capi.CNT_STATUS] != 0:
@@ -147,11 +160,18 @@ class ScanPipeline:
         n = int(counts[f, _capi.CNT_OUTPUT])
         with torch.cuda.stream(ln.stream):
             ln.h_out[:n].copy_(ln.d_out[:n], non_blocking=True)
-            ln.event.record(ln.stream)
-        ln.event.synchronize()
+            ln.copy_event.record(ln.stream)
+        ln.pending = [None, (f, n)]
+        self._d2h_bytes += n * 16 + 32
+
+    def _harvest(self, ln, results, keep_outputs):
+        if ln.pending[1] is None:
+            return
+        f, n = ln.pending[1]
+        ln.copy_event.synchronize()
         if keep_outputs:
             results[f] = ln.h_out[:n].numpy().copy()
-        return n * 16 + 32
+        ln.pending[1] = None
 
     # ---- device resident: inputs already in HBM -----------------------------------------------------
     def prepare_resident(self, pool: torch.Tensor, arena: torch.Tensor | None = None,

@@ -348,9 +348,19 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # measured DRAM bytes per launch (one `ncu --set full` capture of an eager scan, summarised by
+    # profiles/summarise_ncu.py into the newest profiles/*_traffic.json that is committed)
+    traffic, traffic_src = {}, None
+    tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+    if tfiles:
+        tj = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch", {}), f"profiles/{tfiles[-1]}: {tj.get('source', '')}"
+    for k in kernels:
+        k["dram_traffic_MB"] = round(traffic[k["kernel"]] / 1e6, 3) if k["kernel"] in traffic else None
     dom = kernels[0]
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": round(dom["GBps"] / peak, 5) if dom["GBps"] else None, "traffic": None, "peak_source": peak_src,
+                "frac": round(dom["GBps"] / peak, 5) if dom["GBps"] else None,
+                "traffic": traffic.get(dom["kernel"]), "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": dom["share"], "us_per_launch": dom["us_per_launch"],
                 "note": "algorithmic bytes / CUDA-event duration of the dominant kernel, eager launch on its own "
                         "stream, mean over 8 frames; per-kernel table under 'kernels'"}

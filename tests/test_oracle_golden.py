@@ -101,3 +101,33 @@ def test_rgb_helpers_match_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "rgb.npz"))
     assert np.array_equal(pc2.extract_rgb_from_pointcloud(g["merged_float"]), g["extracted"])
     assert np.array_equal(g["extracted"], np.stack([g["r"], g["g"], g["b"]], 1))
+
+
+def test_normals_oracle_solver_against_eigh():
+    """oracle.normals.normal_from_covariance (the analytic symmetric 3x3 solver the CUDA path mirrors)
+    against numpy's eigh on generic, near-planar, exactly planar and needle-shaped neighbourhoods, and
+    the fixed fall-backs (identity covariance -> +z, diagonal -> axis of the smallest entry)."""
+    from oracle import normals as onrm
+    rng = np.random.default_rng(0)
+    for t in range(800):
+        kind = t % 4
+        P = rng.normal(size=(20, 3))
+        if kind == 1:
+            P *= [1.0, 1.0, 1e-3]
+        elif kind == 2:
+            P[:, 2] = 0.3 * P[:, 0] - 0.2 * P[:, 1]
+        elif kind == 3:
+            P = rng.normal(size=(5, 3)) * [1.0, 1e-2, 1e-4]
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        P = P @ R.T + rng.uniform(-50, 50, 3)
+        C = np.cov(P.T, bias=True)
+        n = np.array(onrm.normal_from_covariance(C))
+        w, v = np.linalg.eigh(C)
+        if (w[1] - w[0]) / w[2] > 1e-6:
+            assert abs(abs(n @ v[:, 0]) - 1.0) < 1e-6 and abs(np.linalg.norm(n) - 1.0) < 1e-9
+    assert onrm.normal_from_covariance(np.eye(3)) == [0.0, 0.0, 1.0]
+    assert onrm.normal_from_covariance(np.diag([3.0, 1.0, 2.0])) == [0.0, 1.0, 0.0]
+    pos = rng.uniform(-1, 1, size=(400, 3)).astype(np.float32)
+    pos[:, 2] = 0.25
+    normals, counts, cov = onrm.estimate_normals(pos, 0.3, 30)
+    assert counts.max() <= 30 and np.allclose(np.abs(normals[counts >= 3][:, 2]), 1.0, atol=1e-6)
