@@ -28,10 +28,17 @@ APC_TRACE_EXPORT(neighbors)
 #define CTR_STRAGGLERS 12
 #define CTR_BBOX 14         // 6 ordered-int floats: min xyz, max xyz
 
+// One cell of the open-addressing table: key, population and the start of its run in the sorted
+// array share one 16-byte slot, so a query resolves a cell with ONE 128-bit load (the key probe and
+// the {start, fill} read were two dependent L2 round trips when they lived in separate arrays:
+// 22 % + 14 % of k_radius_query's stall samples, profiles/r1d_ncu_full.csv / hot_sass.py).
+struct __align__(16) GridSlot {
+  unsigned long long key;    // packed (level, ix, iy, iz); all ones = empty
+  uint32_t fill;             // points in the cell
+  uint32_t start;            // first sorted position of the cell
+};
 struct GridDev {
-  unsigned long long* keys;  // [cap]
-  uint32_t* fill;            // [cap] points in the cell
-  uint32_t* start;           // [cap] first sorted position of the cell
+  GridSlot* slots;           // [cap]
   uint32_t cap_mask;
   uint32_t levels;
   uint32_t* slot;            // [levels][n_max] slot of point i at level l
@@ -55,15 +62,27 @@ __device__ __forceinline__ uint64_t grid_key(uint32_t level, int32_t ix, int32_t
   return ((uint64_t)level << 57) | ((uint64_t)(uint32_t)(ix + 262144) << 38) |
          ((uint64_t)(uint32_t)(iy + 262144) << 19) | (uint64_t)(uint32_t)(iz + 262144);
 }
-__device__ __forceinline__ uint32_t grid_find(const GridDev& g, uint64_t key) {
-  uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
+// whole slot in one read-only 128-bit load (the table is not written while a query kernel runs)
+__device__ __forceinline__ uint4 grid_load(const GridDev& g, uint32_t s) {
+  return __ldg(reinterpret_cast<const uint4*>(&g.slots[s]));
+}
+__device__ __forceinline__ uint32_t grid_home(const GridDev& g, uint64_t key) { return (uint32_t)mix64(key) & g.cap_mask; }
+// Finishes a lookup whose first probe (slot s, contents v) is already in registers: run of the
+// cell in [start, start + fill) or false when the cell is empty.
+__device__ __forceinline__ bool grid_resolve(const GridDev& g, uint64_t key, uint32_t s, uint4 v, uint32_t& start,
+                                             uint32_t& fill) {
   for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
-    const unsigned long long k = g.keys[s];
-    if (k == key) return s;
-    if (k == GRID_EMPTY) return GRID_NOSLOT;
+    const uint64_t k = (uint64_t)v.x | ((uint64_t)v.y << 32);
+    if (k == key) { fill = v.z; start = v.w; return true; }
+    if (k == GRID_EMPTY) return false;
     s = (s + 1) & g.cap_mask;
+    v = grid_load(g, s);
   }
-  return GRID_NOSLOT;
+  return false;
+}
+__device__ __forceinline__ bool grid_lookup(const GridDev& g, uint64_t key, uint32_t& start, uint32_t& fill) {
+  const uint32_t s = grid_home(g, key);
+  return grid_resolve(g, key, s, grid_load(g, s), start, fill);
 }
 
 // ---- build ------------------------------------------------------------------------------------
@@ -81,12 +100,12 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
       const uint64_t key = grid_key(level, ix, iy, iz);
       uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
       for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
-        const unsigned long long old = atomicCAS(&g.keys[s], GRID_EMPTY, (unsigned long long)key);
+        const unsigned long long old = atomicCAS(&g.slots[s].key, GRID_EMPTY, (unsigned long long)key);
         if (old == GRID_EMPTY || old == key) { slot = s; break; }
         s = (s + 1) & g.cap_mask;
       }
       if (slot == GRID_NOSLOT) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-      else rank = atomicAdd(&g.fill[slot], 1u);
+      else rank = atomicAdd(&g.slots[slot].fill, 1u);
     } else {
       atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
     }
@@ -109,7 +128,7 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
     uint32_t slot = GRID_NOSLOT, cnt = 0;
     if (i < n) {
       slot = g.slot[(size_t)level * n_max + i];
-      if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) cnt = g.fill[slot];
+      if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) cnt = g.slots[slot].fill;
     }
     uint32_t incl = cnt;
 #pragma unroll
@@ -121,7 +140,7 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
     uint32_t base = 0;
     if (lane == 31 && total) base = atomicAdd(&ctrl->counters[CTR_CURSOR + level], total);
     base = __shfl_sync(0xffffffffu, base, 31);
-    if (cnt) g.start[slot] = base + incl - cnt;
+    if (cnt) g.slots[slot].start = base + incl - cnt;
   }
   APC_STAMP(2, 1);
 }
@@ -135,7 +154,7 @@ k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
     const uint32_t slot = g.slot[(size_t)level * n_max + i];
     if (slot == GRID_NOSLOT) continue;
     const float4 p = pts[i];
-    g.sorted[(size_t)level * n_max + g.start[slot] + g.rank[(size_t)level * n_max + i]] =
+    g.sorted[(size_t)level * n_max + g.slots[slot].start + g.rank[(size_t)level * n_max + i]] =
         make_float4(p.x, p.y, p.z, __uint_as_float(i));
   }
   APC_STAMP(3, 1);
@@ -148,17 +167,18 @@ __global__ void __launch_bounds__(256) k_grid_clean(uint32_t n_max, const uint32
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = g.slot[(size_t)level * n_max + i];
     if (slot != GRID_NOSLOT && g.rank[(size_t)level * n_max + i] == 0) {
-      g.keys[slot] = GRID_EMPTY;
-      g.fill[slot] = 0u;
+      g.slots[slot].key = GRID_EMPTY;
+      g.slots[slot].fill = 0u;
     }
   }
   APC_STAMP(4, 1);
 }
 
-__global__ void k_grid_reset(unsigned long long* keys, uint32_t* fill, uint32_t cap) {
+__global__ void k_grid_reset(GridSlot* slots, uint32_t cap) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
-    keys[s] = GRID_EMPTY;
-    fill[s] = 0u;
+    slots[s].key = GRID_EMPTY;
+    slots[s].fill = 0u;
+    slots[s].start = 0u;
   }
 }
 
@@ -185,16 +205,32 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
     grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
     uint32_t cnt = 0;
     // own cell first, then faces, edges, corners: when only the keep/drop decision is wanted
-    // most points reach nb_points inside their own cell and stop there
+    // most points reach nb_points inside their own cell and stop there.  The first probe of the
+    // NEXT cell is in flight while the current cell's points are scanned.
+    uint64_t key = grid_key(0, ix, iy, iz);
+    uint32_t home = grid_home(g, key);
+    uint4 first = grid_load(g, home);
     for (int c27 = 0; c27 < 27 && (need_counts || cnt < nb_points); ++c27) {
-      const int code = c_cell_order[c27];
-      const int dx = code % 3 - 1, dy = (code / 3) % 3 - 1, dz = code / 9 - 1;
-      const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
-      if (s == GRID_NOSLOT) continue;
-      const uint32_t b = g.start[s], e = b + g.fill[s];
-      for (uint32_t t = b; t < e; ++t) {
-        const float4 p = g.sorted[t];
-        cnt += (d2_f32(q.x, q.y, q.z, p.x, p.y, p.z) <= r2) ? 1u : 0u;
+      const uint64_t key_now = key;
+      const uint32_t home_now = home;
+      const uint4 first_now = first;
+      if (c27 + 1 < 27) {
+        const int code = c_cell_order[c27 + 1];
+        key = grid_key(0, ix + code % 3 - 1, iy + (code / 3) % 3 - 1, iz + code / 9 - 1);
+        home = grid_home(g, key);
+        first = grid_load(g, home);
+      }
+      uint32_t b, f;
+      if (!grid_resolve(g, key_now, home_now, first_now, b, f)) continue;
+      const uint32_t e = b + f;
+      // four points per round: their loads are independent, the exit test runs once per round
+      for (uint32_t t = b; t < e && (need_counts || cnt < nb_points); t += 4) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = g.sorted[min(t + u, e - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          cnt += (t + u < e && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
       }
     }
     mask[orig] = cnt >= nb_points ? 1 : 0;
@@ -245,11 +281,11 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
       for (int dz = -1; dz <= 1; ++dz)
         for (int dy = -1; dy <= 1; ++dy)
           for (int dx = -1; dx <= 1; ++dx, ++t) {
-            const uint32_t s = grid_find(g, grid_key(level, ix + dx, iy + dy, iz + dz));
-            if (s == GRID_NOSLOT) { cs[t] = ce[t] = 0; continue; }
-            cs[t] = g.start[s];
-            ce[t] = cs[t] + g.fill[s];
-            total += ce[t] - cs[t];
+            uint32_t b, f;
+            if (!grid_lookup(g, grid_key(level, ix + dx, iy + dy, iz + dz), b, f)) { cs[t] = ce[t] = 0; continue; }
+            cs[t] = b;
+            ce[t] = b + f;
+            total += f;
           }
       if (total < k_eff) continue;
       // pass 2: exact top-k over the block
@@ -443,7 +479,7 @@ void apc_neighbors_release(apc_ctx* ctx) {
   if (it == g_scratch.end()) return;
   NeighborScratch* s = it->second;
   for (auto& g : s->grid) {
-    void* ptrs[] = {g.d.keys, g.d.fill, g.d.start, g.d.slot, g.d.rank, g.d.sorted, g.d.cell};
+    void* ptrs[] = {g.d.slots, g.d.slot, g.d.rank, g.d.sorted, g.d.cell};
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
@@ -457,16 +493,14 @@ void apc_neighbors_release(apc_ctx* ctx) {
 int apc_neighbors_prepare(apc_ctx* ctx, int which) {
   NeighborScratch* sc = scratch_of(ctx);
   GridHost& g = sc->grid[which];
-  if (g.d.keys) return APC_OK;
+  if (g.d.slots) return APC_OK;
   const uint32_t levels = which == 0 ? 1u : (uint32_t)KNN_LEVELS;
   const size_t M = ctx->max_points;
   uint64_t want = (uint64_t)levels * M * 4 / 3 + 1024;
   uint64_t cap = 1024;
   while (cap < want) cap <<= 1;
   if (which == 0 && cap < ctx->hash_cap) cap = ctx->hash_cap;
-  APC_CUDA(ctx, cudaMalloc((void**)&g.d.keys, cap * sizeof(unsigned long long)));
-  APC_CUDA(ctx, cudaMalloc((void**)&g.d.fill, cap * sizeof(uint32_t)));
-  APC_CUDA(ctx, cudaMalloc((void**)&g.d.start, cap * sizeof(uint32_t)));
+  APC_CUDA(ctx, cudaMalloc((void**)&g.d.slots, cap * sizeof(GridSlot)));
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.slot, (size_t)levels * M * sizeof(uint32_t)));
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.rank, (size_t)levels * M * sizeof(uint32_t)));
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.sorted, (size_t)levels * M * sizeof(float4)));
@@ -474,7 +508,7 @@ int apc_neighbors_prepare(apc_ctx* ctx, int which) {
   g.d.cap_mask = (uint32_t)cap - 1;
   g.d.levels = levels;
   g.cap = (uint32_t)cap;
-  k_grid_reset<<<APC_SM_COUNT * 4, 256>>>(g.d.keys, g.d.fill, (uint32_t)cap);
+  k_grid_reset<<<APC_SM_COUNT * 4, 256>>>(g.d.slots, (uint32_t)cap);
   APC_LAUNCH_CHECK(ctx, "k_grid_reset");
   if (!sc->stragglers) APC_CUDA(ctx, cudaMalloc((void**)&sc->stragglers, M * sizeof(uint32_t)));
   if (!sc->stats) APC_CUDA(ctx, cudaMalloc((void**)&sc->stats, 8 * sizeof(double)));
@@ -485,7 +519,7 @@ int apc_neighbors_prepare(apc_ctx* ctx, int which) {
 int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s) {
   NeighborScratch* sc = scratch_of(ctx);
   for (auto& g : sc->grid)
-    if (g.d.keys) k_grid_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(g.d.keys, g.d.fill, g.cap);
+    if (g.d.slots) k_grid_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(g.d.slots, g.cap);
   APC_LAUNCH_CHECK(ctx, "k_grid_reset");
   return APC_OK;
 }
@@ -566,8 +600,8 @@ k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n
       v[j] = in[i];
       const uint32_t slot = g.slot[i];
       if (slot != GRID_NOSLOT && g.rank[i] == 0) {
-        g.keys[slot] = GRID_EMPTY;
-        g.fill[slot] = 0u;
+        g.slots[slot].key = GRID_EMPTY;
+        g.slots[slot].fill = 0u;
       }
     }
   }
@@ -832,9 +866,9 @@ k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint
     nl.worst = 0;
     for (int c27 = 0; c27 < 27; ++c27) {
       const int dx = c27 % 3 - 1, dy = (c27 / 3) % 3 - 1, dz = c27 / 9 - 1;
-      const uint32_t s = grid_find(g, grid_key(0, ix + dx, iy + dy, iz + dz));
-      if (s == GRID_NOSLOT) continue;
-      const uint32_t b = g.start[s], e = b + g.fill[s];
+      uint32_t b, f;
+      if (!grid_lookup(g, grid_key(0, ix + dx, iy + dy, iz + dz), b, f)) continue;
+      const uint32_t e = b + f;
       for (uint32_t t = b; t < e; ++t) {
         const float4 p = g.sorted[t];
         const float d2 = d2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
