@@ -11,6 +11,7 @@
 //   - a single-thread epilogue applies Open3D's sequential selection / early-stop rule;
 //   - final pass: inlier mask against the winning hypothesis + moment sums for the
 //     least-squares refit, reduced in a fixed order.
+#include <cstdlib>
 #include "apc_scan.cuh"
 APC_TRACE_EXPORT(ransac)
 
@@ -607,8 +608,13 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const uint32_t pad16 = apc_div_up(iters, 16) * 16, pad20 = apc_div_up(iters, 20) * 20;
   const uint32_t ch = pad20 < pad16 ? 20u : 16u;
   const uint32_t n_chunks = apc_div_up(iters, ch);
-  // ~2 resident CTAs per SM in total, each striding over the same number of point tiles
-  const uint32_t gx0 = min(n_tiles, max(1u, (uint32_t)(APC_SM_COUNT * 2) / n_chunks));
+  // ONE resident CTA per SM in total, each striding over the same number of point tiles.  The
+  // kernel's own duration is the same with two (27.6 vs 27.9 us: prologue, flush and selection do
+  // not shrink), but at 124 registers two CTAs own an SM's whole register file and shut the other
+  // lanes' kernels out: one per SM measured 74.9 instead of 77.2 us/scan with 8 lanes.
+  // APC_RS_HALF_CTAS_PER_SM (in half CTAs per SM) overrides for experiments.
+  static const uint32_t ctas_x2 = []() { const char* e = getenv("APC_RS_HALF_CTAS_PER_SM"); return e ? min(max((uint32_t)atoi(e), 1u), 4u) : 2u; }();   // the tally rows are sized for <= 2 CTAs per SM
+  const uint32_t gx0 = min(n_tiles, max(1u, (uint32_t)(APC_SM_COUNT * ctas_x2 / 2) / n_chunks));
   const uint32_t gx = apc_div_up(n_tiles, apc_div_up(n_tiles, gx0));
   const dim3 grid(gx, n_chunks);
   {

@@ -120,6 +120,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def algorithmic_bytes(kernel: str, c) -> float | None:
     """Algorithmic HBM bytes of one launch (DESIGN.md section 'Kernels'), from the measured
     per-frame counts: N input, M filtered, V voxels, P after radius, ps = point_step."""
@@ -170,7 +183,7 @@ def run_reference(args, rank, world):
                                    f"scipy cKDTree workers=-1 ({cores} cores, torch threads {torch.get_num_threads()})"},
         "e2e": {"value": round(value, 4), "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -183,6 +196,12 @@ def main():
     ap.add_argument("--lanes", type=int, default=8, help="concurrent stream lanes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # exactly ONE line on stdout: libraries that print to fd 1 (NCCL's version banner when the
+    # box sets NCCL_DEBUG) are sent to stderr; the JSON line goes to the real stdout at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,7 +412,7 @@ def main():
         "kernels_per_scan": int(pipe.kernels_per_scan),
         "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
