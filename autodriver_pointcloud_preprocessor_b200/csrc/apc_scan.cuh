@@ -39,14 +39,20 @@ __device__ __forceinline__ uint32_t scan_wait(const uint64_t* word, uint32_t ep)
 // (n^2/2 polled words): what costs is the number of threads polling the same lines.
 // Called by all threads of the CTA; relies on CTAs being dispatched in blockIdx order (lower
 // tiles are resident or finished whenever a tile waits).  smem: one uint32_t.
-__device__ __forceinline__ uint32_t scan_two_level(uint64_t* __restrict__ state, uint32_t tile, uint32_t n_tiles,
-                                                   uint32_t epoch, uint32_t total, uint32_t* smem1) {
+// Step 1 alone (one thread): lets a kernel put independent work between publishing its total and
+// waiting for its predecessors', so that the successors are not held up by that work.
+__device__ __forceinline__ void scan_publish(uint64_t* __restrict__ state, uint32_t tile, uint32_t epoch, uint32_t total) {
+  st_volatile_u64(&state[APC_SCAN_GROUPS + tile], scan_pack(epoch & 0x3fffffffu, APC_ST_VALID, total));
+}
+template <bool PUBLISHED>
+__device__ __forceinline__ uint32_t scan_two_level_impl(uint64_t* __restrict__ state, uint32_t tile, uint32_t n_tiles,
+                                                        uint32_t epoch, uint32_t total, uint32_t* smem1) {
   const uint32_t ep = epoch & 0x3fffffffu;
   if (threadIdx.x < 32) {
     const uint32_t lane = threadIdx.x;
     const uint32_t group = tile / APC_SCAN_GROUP, r = tile % APC_SCAN_GROUP;
     uint64_t* totals = state + APC_SCAN_GROUPS;
-    if (lane == 0) st_volatile_u64(&totals[tile], scan_pack(ep, APC_ST_VALID, total));
+    if (!PUBLISHED && lane == 0) st_volatile_u64(&totals[tile], scan_pack(ep, APC_ST_VALID, total));
     uint32_t v = 0;
     if (lane < r) v = scan_wait(&totals[group * APC_SCAN_GROUP + lane], ep);
     const uint32_t in_group = warp_sum_u32(v);
@@ -62,6 +68,10 @@ __device__ __forceinline__ uint32_t scan_two_level(uint64_t* __restrict__ state,
   }
   __syncthreads();
   return *smem1;
+}
+__device__ __forceinline__ uint32_t scan_two_level(uint64_t* __restrict__ state, uint32_t tile, uint32_t n_tiles,
+                                                   uint32_t epoch, uint32_t total, uint32_t* smem1) {
+  return scan_two_level_impl<false>(state, tile, n_tiles, epoch, total, smem1);
 }
 
 // Order-preserving ranks for a striped tile: item j of thread t is tile element j*256+t.

@@ -1,6 +1,7 @@
 // Context lifecycle, scratch sizing, error reporting (apc.h lifecycle section).
 // Replaces the reference's per-node device/point-cloud setup (pp.py:272-280, pp.py:309).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "apc_common.cuh"
@@ -94,7 +95,10 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   ctx->device = device;
   ctx->max_points = max_points;
   const size_t M = max_points;
-  ctx->hash_cap = next_pow2(4ull * M);   // load factor <= 0.25: short probe chains (the warp-wide worst chain sets the latency)
+  // load factor <= 0.25: short probe chains (the warp-wide worst chain sets the latency).
+  // APC_HASH_SLOTS_PER_POINT overrides for experiments.
+  const char* lf = getenv("APC_HASH_SLOTS_PER_POINT");
+  ctx->hash_cap = next_pow2((lf && atoi(lf) >= 2 ? (uint64_t)atoi(lf) : 4ull) * M);
   const size_t C = ctx->hash_cap;
   ctx->max_tiles = apc_div_up((uint32_t)(C > M ? C : M), 1024) + 8;
   ctx->rs_max_iters = 4096;

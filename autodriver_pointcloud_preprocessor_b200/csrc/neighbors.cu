@@ -16,10 +16,9 @@
 // are (fewer than k points in range of the coarsest level) fall to an exact brute-force
 // kernel.  The table is cleaned by the points that own rank 0 of their cell, not by memset.
 #include "apc_scan.cuh"
+#include "apc_grid.cuh"
 APC_TRACE_EXPORT(neighbors)
 
-#define GRID_EMPTY 0xffffffffffffffffull
-#define GRID_NOSLOT 0xffffffffu
 #define KNN_LEVELS 12
 #define KNN_KMAX 64
 
@@ -28,40 +27,6 @@ APC_TRACE_EXPORT(neighbors)
 #define CTR_STRAGGLERS 12
 #define CTR_BBOX 14         // 6 ordered-int floats: min xyz, max xyz
 
-// One cell of the open-addressing table: key, population and the start of its run in the sorted
-// array share one 16-byte slot, so a query resolves a cell with ONE 128-bit load (the key probe and
-// the {start, fill} read were two dependent L2 round trips when they lived in separate arrays:
-// 22 % + 14 % of k_radius_query's stall samples, profiles/r1d_ncu_full.csv / hot_sass.py).
-struct __align__(16) GridSlot {
-  unsigned long long key;    // packed (level, ix, iy, iz); all ones = empty
-  uint32_t fill;             // points in the cell
-  uint32_t start;            // first sorted position of the cell
-};
-struct GridDev {
-  GridSlot* slots;           // [cap]
-  uint32_t cap_mask;
-  uint32_t levels;
-  uint32_t* slot;            // [levels][n_max] slot of point i at level l
-  uint32_t* rank;            // [levels][n_max] arrival rank of point i inside its cell
-  float4* sorted;            // [levels][n_max] xyz + original index (bits in w)
-  float* cell;               // [levels] cell sizes (device)
-  float cell0;               // > 0: single-level grid whose cell size the host knows (no k_grid_cells launch)
-};
-__device__ __forceinline__ float grid_cell_size(const GridDev& g, uint32_t level) {
-  return g.cell0 > 0.0f ? g.cell0 : g.cell[level];
-}
-
-__device__ __forceinline__ bool grid_coord(float x, float y, float z, float c, int32_t& ix, int32_t& iy, int32_t& iz) {
-  const float qx = floorf(__fdiv_rn(x, c)), qy = floorf(__fdiv_rn(y, c)), qz = floorf(__fdiv_rn(z, c));
-  const float h = 262143.0f;  // one cell of margin for the +-1 neighbour offsets
-  if (!(qx >= -h && qx < h && qy >= -h && qy < h && qz >= -h && qz < h)) return false;
-  ix = (int32_t)qx; iy = (int32_t)qy; iz = (int32_t)qz;
-  return true;
-}
-__device__ __forceinline__ uint64_t grid_key(uint32_t level, int32_t ix, int32_t iy, int32_t iz) {
-  return ((uint64_t)level << 57) | ((uint64_t)(uint32_t)(ix + 262144) << 38) |
-         ((uint64_t)(uint32_t)(iy + 262144) << 19) | (uint64_t)(uint32_t)(iz + 262144);
-}
 // whole slot in one read-only 128-bit load (the table is not written while a query kernel runs)
 __device__ __forceinline__ uint4 grid_load(const GridDev& g, uint32_t s) {
   return __ldg(reinterpret_cast<const uint4*>(&g.slots[s]));
@@ -94,21 +59,8 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
   APC_STAMP(1, 0);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
-    int32_t ix, iy, iz;
-    uint32_t slot = GRID_NOSLOT, rank = 0;
-    if (grid_coord(p.x, p.y, p.z, c, ix, iy, iz)) {
-      const uint64_t key = grid_key(level, ix, iy, iz);
-      uint32_t s = (uint32_t)mix64(key) & g.cap_mask;
-      for (uint32_t probe = 0; probe <= g.cap_mask; ++probe) {
-        const unsigned long long old = atomicCAS(&g.slots[s].key, GRID_EMPTY, (unsigned long long)key);
-        if (old == GRID_EMPTY || old == key) { slot = s; break; }
-        s = (s + 1) & g.cap_mask;
-      }
-      if (slot == GRID_NOSLOT) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
-      else rank = atomicAdd(&g.slots[slot].fill, 1u);
-    } else {
-      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
-    }
+    uint32_t slot, rank;
+    grid_insert_point(g, level, p.x, p.y, p.z, c, ctrl, slot, rank);
     g.slot[(size_t)level * n_max + i] = slot;
     g.rank[(size_t)level * n_max + i] = rank;
   }
@@ -525,7 +477,7 @@ int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s) {
 }
 
 static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_max, const uint32_t* n_dev,
-                      float cell_hint, bool need_bbox, cudaStream_t s) {
+                      float cell_hint, bool need_bbox, cudaStream_t s, bool inserted = false) {
   const uint32_t bx = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
   if (need_bbox) {
     k_bbox_init<<<1, 32, 0, s>>>(ctx->ctrl);
@@ -534,7 +486,7 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
   g.d.cell0 = (g.d.levels == 1 && cell_hint > 0.0f) ? cell_hint : 0.0f;
   if (!(g.d.cell0 > 0.0f)) k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
   const dim3 grid(bx, g.d.levels);
-  {
+  if (!inserted) {   // (the pipeline's voxel stage inserts its centroids as it writes them)
     APC_PROF(ctx, "k_grid_insert", s);
     k_grid_insert<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d, ctx->ctrl);
   }
@@ -613,9 +565,21 @@ k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n
 }
 
 // radius outlier removal + select_by_mask for the pipeline: query, then the fused select/clean
+// Device view of the context's radius grid with the cell size of `radius` set: for a producer
+// kernel in another file that inserts its output points itself (grid_insert_point) and then calls
+// apc_radius_select_nobegin with points_inserted = 1.  Allocates on first use (not under capture).
+int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
+  int rc = apc_neighbors_prepare(ctx, 0);
+  if (rc) return rc;
+  GridHost& g = scratch_of(ctx)->grid[0];
+  g.d.cell0 = (float)radius * 1.0009765625f;
+  *out = g.d;
+  return APC_OK;
+}
+
 int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_points,
                               double radius, uint8_t* mask_scratch, float* out_xyzi, uint32_t* out_count_dev,
-                              int scan_slot, cudaStream_t s) {
+                              int scan_slot, int points_inserted, cudaStream_t s) {
   APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
   if (n_max == 0) {
     APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
@@ -629,7 +593,7 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   GridHost& g = scratch_of(ctx)->grid[0];
   const float r32 = (float)radius;
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
-  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s, points_inserted != 0);
   if (rc) return rc;
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   {

@@ -2,18 +2,21 @@
 // statistical outliers -> radius outliers -> RANSAC ground removal, chained through device
 // counters so that no stage waits for the host, plus CUDA-graph capture / replay of the
 // whole chain (one launch per scan).
-#include "apc_common.cuh"
+#include <cstdlib>
+
+#include "apc_grid.cuh"
 APC_TRACE_EXPORT(pipeline)
 
 // stage entry points without the per-call epoch bump (defined in the stage files)
 int apc_frontend_nobegin(apc_ctx*, const apc_cloud_desc*, uint32_t, const apc_filter_cfg*, float*, uint32_t*, uint8_t*,
                          uint32_t*, int, cudaStream_t);
 int apc_voxel_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, float, float*, int32_t*, uint32_t*, uint32_t*,
-                      int, cudaStream_t);
+                      int, const GridDev*, cudaStream_t);
+int apc_radius_grid_view(apc_ctx*, double, GridDev*);
 int apc_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, const uint8_t*, int, float*, uint32_t*,
                        uint32_t*, int, cudaStream_t);
 int apc_radius_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, float*, uint32_t*, int,
-                              cudaStream_t);
+                              int, cudaStream_t);
 int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
@@ -64,9 +67,19 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   uint32_t cur_cnt = DC_FILTERED;
   rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, nullptr, nullptr, dc + DC_FILTERED, 0, s);
   if (rc) return rc;
+  // voxel -> radius with nothing in between: the voxel stage inserts its centroids into the radius
+  // grid as it writes them (one launch and one pass over the centroids less)
+  static const bool fuse_grid = getenv("APC_NO_GRID_FUSION") == nullptr;   // A/B knob for profiles/
+  const bool grid_in_voxel = fuse_grid && has_vox && has_rad && !has_stat && n_total > 0;
   if (has_vox) {
     float* out = dst();
-    rc = apc_voxel_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->voxel_size, out, nullptr, nullptr, dc + DC_VOXELS, 1, s);
+    GridDev grid{};
+    if (grid_in_voxel) {
+      rc = apc_radius_grid_view(ctx, cfg->radius_search_radius, &grid);
+      if (rc) return rc;
+    }
+    rc = apc_voxel_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->voxel_size, out, nullptr, nullptr, dc + DC_VOXELS, 1,
+                           grid_in_voxel ? &grid : nullptr, s);
     if (rc) return rc;
     cur = out;
     cur_cnt = DC_VOXELS;
@@ -86,7 +99,7 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     float* out = dst();
     // the select_by_mask of the radius decision also cleans the neighbour grid (one launch)
     rc = apc_radius_select_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
-                                   ctx->mask_a, out, dc + DC_RADIUS, 3, s);
+                                   ctx->mask_a, out, dc + DC_RADIUS, 3, grid_in_voxel ? 1 : 0, s);
     if (rc) return rc;
     cur = out;
     cur_cnt = DC_RADIUS;

@@ -12,6 +12,7 @@
 // The table is self-cleaning: the thread that finalises a voxel resets its slot, so no
 // per-frame memset of the (capacity x 52 B) table sits on the critical path.
 #include "apc_scan.cuh"
+#include "apc_grid.cuh"
 APC_TRACE_EXPORT(voxel)
 
 #define VOX_EMPTY 0xffffffffffffffffull
@@ -90,11 +91,15 @@ __device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, 
 // centroid (owner's coordinates + the joiners' sums, exact integers, one float64 divide) is
 // computed BEFORE the cross-tile scan so that the slot and owner loads overlap the scan's wait;
 // after the scan only stores remain.
+// GRID: the pipeline's next stage is radius outlier removal - every centroid is inserted into the
+// neighbour grid right here (cell claim + arrival rank, whose atomics also overlap the scan's wait)
+// and the stand-alone k_grid_insert pass over the centroids is not launched.
+template <bool GRID>
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
                  VoxSlot* __restrict__ slots, uint32_t* __restrict__ rank_of_slot,
                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
-                 uint64_t* scan_state, ApcCtrl* ctrl, uint32_t n_tiles) {
+                 uint64_t* scan_state, ApcCtrl* ctrl, uint32_t n_tiles, const __grid_constant__ GridDev grid) {
   __shared__ uint32_t sm_scan[34];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
@@ -116,6 +121,7 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
   for (int j = 0; j < APC_TILE_ITEMS; ++j) owner[j] = slot[j] != VOX_NOSLOT ? slots[slot[j]].owner : 0u;
   float4 cen[APC_TILE_ITEMS];
   uint32_t npts[APC_TILE_ITEMS];
+  uint32_t gslot[APC_TILE_ITEMS], grank[APC_TILE_ITEMS];
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
@@ -138,7 +144,13 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
   }
   uint32_t rank[APC_TILE_ITEMS];
   APC_STAMP(1, 1);
-  const uint32_t base = tile_compact_offsets(is_first, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+  // ranks inside the tile, publish the tile's total, THEN the grid atomics (the successors' wait
+  // does not include them), then collect the predecessors' totals
+  const uint32_t total = tile_ranks(is_first, rank, sm_scan);
+  if (threadIdx.x == 0) scan_publish(scan_state, tile, epoch, total);
+  if (GRID) grid_insert_items<APC_TILE_ITEMS>(grid, 0, is_first, cen, grid.cell0, ctrl, gslot, grank);
+  const uint32_t base = scan_two_level_impl<true>(scan_state, tile, n_tiles, epoch, total, &sm_scan[33]);
+  if (threadIdx.x == 0 && tile == n_tiles - 1 && out_count) *out_count = base + total;
   APC_STAMP(1, 2);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j) {
@@ -146,6 +158,10 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
       const uint32_t s = slot[j];
       const uint32_t r = base + rank[j];
       out[r] = cen[j];
+      if (GRID) {
+        grid.slot[r] = gslot[j];
+        grid.rank[r] = grank[j];
+      }
       if (out_counts) out_counts[r] = npts[j];
       rank_of_slot[s] = r;
       // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0, acc = 0}
@@ -184,9 +200,10 @@ int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s) {
   return APC_OK;
 }
 
+// `radius_grid`: when non-NULL the centroids are also inserted into that neighbour grid (see GRID above).
 int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, float voxel_size,
                       float* out_xyzi, int32_t* out_p2v, uint32_t* out_voxel_counts, uint32_t* out_count_dev,
-                      int scan_slot, cudaStream_t s) {
+                      int scan_slot, const GridDev* radius_grid, cudaStream_t s) {
   APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
   APC_REQUIRE(ctx, voxel_size > 0.0f, "voxel_size must be > 0");
   if (n_max == 0) {
@@ -205,9 +222,16 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_PROF(ctx, "k_voxel_finalize", s);
-  k_voxel_finalize<<<n_tiles, APC_TILE_THREADS, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
-                                                        reinterpret_cast<float4*>(out_xyzi), out_voxel_counts,
-                                                        out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
+  if (radius_grid)
+    k_voxel_finalize<true><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
+        reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
+        n_tiles, *radius_grid);
+  else
+    k_voxel_finalize<false><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
+        reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
+        n_tiles, GridDev{});
   APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
   if (out_p2v) {
     k_voxel_p2v<<<blocks, 256, 0, s>>>(n_max, n_dev, ctx->p2slot, ctx->vox_rank, out_p2v);
@@ -223,7 +247,8 @@ extern "C" int apc_voxel_downsample(apc_ctx* ctx, const float* xyzi, uint32_t n_
   cudaStream_t s = (cudaStream_t)stream;
   int rc = apc_begin(ctx, s);
   if (rc) return rc;
-  return apc_voxel_nobegin(ctx, xyzi, n_max, n_dev, voxel_size, out_xyzi, out_p2v, out_voxel_counts, out_count_dev, 1, s);
+  return apc_voxel_nobegin(ctx, xyzi, n_max, n_dev, voxel_size, out_xyzi, out_p2v, out_voxel_counts, out_count_dev, 1,
+                           nullptr, s);
 }
 
 // Per-attribute voxel mean, Open3D style: float32 sums (atomics), then sum / count in float32.

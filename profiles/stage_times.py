@@ -14,6 +14,9 @@ import bench  # noqa: E402
 from autodriver_pointcloud_preprocessor_b200 import _capi, replay  # noqa: E402
 
 n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+if len(sys.argv) > 2:                    # azimuth steps per scan: 2048 = C2 (262144 points), 8192 = 1 Mi points
+    bench.N_AZ = int(sys.argv[2])
+    bench.N_POINTS = bench.N_BEAMS * bench.N_AZ
 msgs = bench.make_frames(n_frames, seed0=0)
 filter_kw = dict(skip_nans=True, dedup_mode=_capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True,
                  transforms=[bench.TF], crop=bench.CROP)
@@ -42,5 +45,11 @@ with torch.cuda.stream(ln.stream):
             lat.append(a.elapsed_time(b) * 1e3)
 tot = sum(v[0] / v[1] for v in prof.values())
 print(f"graph p50 {np.median(lat):.1f} us   sum of kernels {tot * 1e3:.1f} us   kernels/scan {pipe.kernels_per_scan}")
+counts = ln.d_counts.cpu().numpy().astype(float)
+cnt = {"N": counts[_capi.CNT_INPUT], "M": counts[_capi.CNT_FILTERED], "V": counts[_capi.CNT_VOXELS],
+       "P_radius_in": counts[_capi.CNT_VOXELS], "P_ground_in": counts[_capi.CNT_AFTER_RADIUS], "out": counts[_capi.CNT_OUTPUT]}
+print(f"points per scan {bench.N_POINTS}: " + ", ".join(f"{k}={int(v)}" for k, v in cnt.items()))
 for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-    print(f"  {k:22s} {ms / n * 1e3:8.2f} us")
+    ab = bench.algorithmic_bytes(k, cnt)
+    gbs = f"{ab / (ms / n * 1e-3) / 1e9:8.1f} GB/s algorithmic" if ab else ""
+    print(f"  {k:22s} {ms / n * 1e3:8.2f} us {gbs}")
