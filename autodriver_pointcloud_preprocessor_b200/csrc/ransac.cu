@@ -536,17 +536,22 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     for (int j = 0; j < APC_TILE_ITEMS; ++j)
       if (keep[j]) keep_out[base + rank[j]] = p[j];
   }
+  // tiles past the device-side count hold no points: no partial row (the last CTA reads only the
+  // rows of the tiles in use - adding their zeros would not change a bit of the sums)
+  const uint32_t used_tiles = min(gridDim.x, (P + APC_TILE_POINTS - 1) / APC_TILE_POINTS);
+  if (blockIdx.x < used_tiles) {
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < 10; ++k) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (lane_id() == 0) s_red[threadIdx.x >> 5][k] = acc[k];
-  }
-  __syncthreads();
-  if (threadIdx.x < 10) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * 10 + threadIdx.x] = s;
+      for (int o = 1; o < 32; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      if (lane_id() == 0) s_red[threadIdx.x >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+      partials[(size_t)blockIdx.x * 10 + threadIdx.x] = s;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) s_last = (ticket_acq_rel(&ctrl->counters[CTR_RS_TICKET]) == gridDim.x - 1);
@@ -559,8 +564,8 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   __shared__ double s_tot[10];
   double run = 0.0;
   const volatile double* vp = partials;
-  for (uint32_t b0 = 0; b0 < gridDim.x; b0 += 256) {
-    const uint32_t rows = min(256u, gridDim.x - b0);
+  for (uint32_t b0 = 0; b0 < used_tiles; b0 += 256) {
+    const uint32_t rows = min(256u, used_tiles - b0);
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < rows * 10; e += blockDim.x) s_part[e] = vp[(size_t)b0 * 10 + e];
     __syncthreads();

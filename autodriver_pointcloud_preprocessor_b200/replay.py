@@ -47,6 +47,44 @@ def gather_outputs(send: torch.Tensor, counts: torch.Tensor, group=None):
     return recv, all_counts
 
 
+class PeerGather:
+    """The same all-gather by peer-to-peer copies over NVLink, double buffered: every lane stages a
+    frame's output rows straight into this rank's slot of a symmetric buffer (``slot(parity)``), and
+    ``gather(parity)`` pushes that slot into the same slot of every peer's buffer with the copy
+    engines, bracketed by two signal-pad barriers - while the next step fills the other parity.
+    NCCL's all-gather kernels take SMs away from the scan kernels that run underneath and need a
+    staging copy on the compute stream; copy-engine traffic needs neither.  The per-frame counts
+    stay on NCCL.
+
+    Needs ``torch.distributed._symmetric_memory`` and peer access between the GPUs of the node;
+    construct inside ``try`` and fall back to :func:`gather_outputs` when it raises.
+    """
+
+    def __init__(self, slab_shape, dtype, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf = symm.empty((2, self.world) + tuple(slab_shape), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.peers = [self.hdl.get_buffer(p, tuple(self.buf.shape), dtype) for p in range(self.world)]
+
+    def slot(self, parity: int) -> torch.Tensor:
+        """This rank's [F, rows, 4] staging slab of the given parity (local memory)."""
+        return self.buf[parity][self.rank]
+
+    def gather(self, parity: int) -> torch.Tensor:
+        """Issue on the current stream; returns the local [G, F, rows, 4] buffer of that parity
+        (complete, in stream order, once this call's second barrier has passed)."""
+        self.hdl.barrier(channel=0)                       # every peer is done with this parity's previous contents
+        src = self.buf[parity][self.rank]
+        for k in range(1, self.world):                    # rank+1, rank+2, ...: no hot spot
+            p = (self.rank + k) % self.world
+            self.peers[p][parity][self.rank].copy_(src, non_blocking=True)
+        self.hdl.barrier(channel=1)                       # every rank's slabs have landed everywhere
+        return self.buf[parity]
+
+
 class _Lane:
     __slots__ = ("stream", "ctx", "d_in", "d_out", "d_counts", "d_plane", "h_counts", "h_out", "graph",
                  "resident_graphs", "pending", "event", "copy_event", "desc")
@@ -180,18 +218,23 @@ class ScanPipeline:
         replaying reads each frame in place.  With ``arena`` [F, n_points, 4] / ``counts_arena``
         [F, 8] every frame writes its own output slot (needed for the multi-GPU gather)."""
         self._pool = pool
+        self._resident_out = {}
         S = len(self.lanes)
         for f in range(pool.shape[0]):
             ln = self.lanes[f % S]
             desc = engine.make_cloud_desc(self.fields, self.point_step, self.n_points, pool[f])
             out = arena[f] if arena is not None else ln.d_out
             cnt = counts_arena[f] if counts_arena is not None else ln.d_counts
+            self._resident_out[f] = out
             ln.resident_graphs[f] = ln.ctx.capture_pipeline([desc], self.pcfg, out, cnt, ln.d_plane)
         torch.cuda.synchronize(self.device)
 
-    def run_resident(self, frame_ids, main_stream=None):
+    def run_resident(self, frame_ids, main_stream=None, stage_to: torch.Tensor | None = None):
         """Replay the captured graphs for ``frame_ids`` across the lanes.  The caller's current
-        stream is the fork/join point, so CUDA events recorded on it bracket the whole batch."""
+        stream is the fork/join point, so CUDA events recorded on it bracket the whole batch.
+        ``stage_to`` [F, rows, 4]: each lane also copies the first ``rows`` rows of the frame's
+        output into ``stage_to[f]`` right behind the frame's graph (a copy-engine copy on the lane's
+        own stream), e.g. into the slab the multi-GPU gather sends."""
         main = torch.cuda.current_stream(self.device) if main_stream is None else main_stream
         S = len(self.lanes)
         fork = torch.cuda.Event()
@@ -202,6 +245,8 @@ class ScanPipeline:
             ln = self.lanes[f % S]
             with torch.cuda.stream(ln.stream):
                 ln.ctx.launch_graph(ln.resident_graphs[f])
+                if stage_to is not None:
+                    stage_to[f].copy_(self._resident_out[f][:stage_to.shape[1]], non_blocking=True)
         for ln in self.lanes:
             ln.event.record(ln.stream)
             main.wait_event(ln.event)

@@ -229,31 +229,48 @@ def main():
     pipe = replay.ScanPipeline(msgs[0].fields, POINT_STEP, N_POINTS, filter_kw, STAGES, lanes=args.lanes,
                                device=local_rank)
     arena = counts_arena = None
-    if world > 1:
+    if os.environ.get("APC_FORCE_ARENA"):                          # diagnostic: one output buffer per frame
         arena = torch.zeros((F, N_POINTS, 4), dtype=torch.float32, device=dev)
     counts_arena = torch.zeros((F, 8), dtype=torch.int32, device=dev)
     pipe.prepare_resident(pool, arena, counts_arena)
     frame_ids = list(range(F))
     main_stream = torch.cuda.current_stream(dev)
 
-    # multi-GPU: all-gather the outputs of step k on a side stream while step k+1 computes
+    # multi-GPU: every lane stages a frame's output rows into the send slab of the step's parity right
+    # behind the frame's graph; the all-gather of step k's slab runs on a side stream underneath step
+    # k+1, which fills the other parity
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    pad_rows, send = 0, None
+    pad_rows, send2 = 0, None
+    send_counts = torch.zeros(F, dtype=torch.int32, device=dev) if world > 1 else None
+    all_counts = torch.zeros((world, F), dtype=torch.int32, device=dev) if world > 1 else None
+    peer_gather, gather_how = None, "NCCL all-gather"
+    gather_done = [None, None]
+    step_no = 0
+    no_gather = os.environ.get("APC_GATHER") == "none"               # diagnostic: attribute the gather's cost
 
-    def gather_step():
-        nonlocal send
+    def step():
+        nonlocal step_no
+        if world == 1 or no_gather or send2 is None:
+            pipe.run_resident(frame_ids, main_stream)
+            return
+        parity = step_no & 1
+        step_no += 1
+        if gather_done[parity] is not None:
+            main_stream.wait_event(gather_done[parity])          # the gather two steps back has sent this slab
+        slab = peer_gather.slot(parity) if peer_gather is not None else send2[parity]
+        pipe.run_resident(frame_ids, main_stream, stage_to=slab)
+        send_counts.copy_(counts_arena[:, _capi.CNT_OUTPUT])
         done = torch.cuda.Event()
         done.record(main_stream)
         comm_stream.wait_event(done)
         with torch.cuda.stream(comm_stream):
-            send.copy_(arena[:, :pad_rows])
-            replay.gather_outputs(send, counts_arena[:, _capi.CNT_OUTPUT].contiguous())
-
-    def step():
-        pipe.run_resident(frame_ids, main_stream)
-        if world > 1:
-            main_stream.wait_stream(comm_stream)      # previous gather has consumed the arena
-            gather_step()
+            if peer_gather is not None:
+                peer_gather.gather(parity)
+                dist.all_gather_into_tensor(all_counts, send_counts)
+            else:
+                replay.gather_outputs(slab, send_counts)
+            gather_done[parity] = torch.cuda.Event()
+            gather_done[parity].record(comm_stream)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -268,7 +285,13 @@ def main():
         mx = torch.tensor([int(counts0[:, _capi.CNT_OUTPUT].max())], device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         pad_rows = min(N_POINTS, (int(mx.item()) * 9 // 8 + 1023) // 1024 * 1024)
-        send = torch.zeros((F, pad_rows, 4), dtype=torch.float32, device=dev)
+        if os.environ.get("APC_GATHER", "peer") == "peer":
+            try:
+                peer_gather = replay.PeerGather((F, pad_rows, 4), torch.float32, dev)
+                gather_how = "peer-to-peer copy-engine writes over NVLink into symmetric buffers + NCCL counts"
+            except Exception as e:                                               # no symmetric memory / peer access
+                print(f"PeerGather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+        send2 = True if peer_gather is not None else torch.zeros((2, F, pad_rows, 4), dtype=torch.float32, device=dev)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(dev)
@@ -401,7 +424,7 @@ def main():
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "lanes": args.lanes,
                    "input_bytes_per_step_per_gpu": F * N_POINTS * POINT_STEP,
                    "l2": "inputs larger than L2 (268 MB of distinct scans per step vs 126 MB L2)",
-                   "multi_gpu": "frame-parallel, no per-scan collective; per-step NCCL all-gather of outputs "
+                   "multi_gpu": f"frame-parallel, no per-scan collective; per-step all-gather of outputs ({gather_how}) "
                                 "overlapped with the next step" if world > 1 else "single GPU"},
         "p50_latency_ms": round(float(np.median(lat)), 4), "p99_latency_ms": round(float(np.percentile(lat, 99)), 4),
         "p50_latency_e2e_ms": round(float(np.median(lat_e2e)), 4),
