@@ -121,6 +121,27 @@ class ClockSampler(threading.Thread):
 
 
 _REAL_STDOUT = None
+_ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs NVML
+    reports as local to its GPU: with 8 ranks on a two-socket box the end-to-end path otherwise moves
+    half of its PCIe traffic across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        global _ORIG_AFFINITY
+        _ORIG_AFFINITY = set(os.sched_getaffinity(0))
+        cpus &= _ORIG_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:                                                 # best effort: NVML / affinity not available
+        pass
 
 
 def emit(line: dict):
@@ -214,6 +235,7 @@ def main():
     from autodriver_pointcloud_preprocessor_b200 import _capi, replay
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -409,10 +431,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
+        if _ORIG_AFFINITY:                                                      # the CPU baseline gets every host core back
+            os.sched_setaffinity(0, _ORIG_AFFINITY)
         n_cpu = 3
         cpu_pipeline_seconds(msgs[:1])                                           # warm-up (thread pools, imports)
         secs, _ = cpu_pipeline_seconds(msgs[:n_cpu])
-        cpu = {"value": round(n_cpu * N_POINTS / secs / 1e6, 4), "unit": "Mpoints/s", "cores": os.cpu_count(),
+        cpu = {"value": round(n_cpu * N_POINTS / secs / 1e6, 4), "unit": "Mpoints/s", "cores": len(os.sched_getaffinity(0)),
                "kind": "port", "ms_per_scan": round(secs / n_cpu * 1e3, 1),
                "sample": f"{n_cpu} scans of the same workload through oracle/pipeline.py (numpy + scipy cKDTree "
                          f"workers=-1) after 1 warm-up scan"}
