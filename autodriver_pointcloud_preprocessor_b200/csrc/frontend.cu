@@ -8,6 +8,8 @@
 // pp.py:469 (remove_non_finite_points), pp.py:482,487,490 (transform), utils.py:240-301
 // (crop_pointcloud), utils.py:271,297 + pp.py:542 (select_by_mask / select_by_index),
 // pointcloud_concatenator.py:1-5 (merge N sensors into one cloud in a target frame).
+#include <cstdlib>
+
 #include "apc_load.cuh"
 APC_TRACE_EXPORT(frontend)
 
@@ -389,7 +391,10 @@ static int build_params(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     }
   }
   prm.slots = ctx->dedup_slots;
-  prm.slot_mask = ctx->hash_cap - 1;
+  // the duplicate table is all touched once per scan (4 slots per 32-byte sector, one point in four
+  // slots): APC_DEDUP_SHRINK = 1 uses half of it (load 0.5, half the sectors), 0 all of it
+  static const uint32_t shrink = []() { const char* e = getenv("APC_DEDUP_SHRINK"); return e ? (uint32_t)atoi(e) & 3u : 0u; }();
+  prm.slot_mask = (ctx->hash_cap >> shrink) - 1;
   prm.p2slot = ctx->p2slot;
   prm.ctrl = ctx->ctrl;
   *total_points = points;

@@ -113,12 +113,17 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
     slot[j] = i < n ? p2slot[i] : VOX_NOSLOT;
   }
-#pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j)   // {key lo, key hi, first, cnt}: all four loads in flight
-    head[j] = slot[j] != VOX_NOSLOT ? *reinterpret_cast<const uint4*>(&slots[slot[j]]) : make_uint4(0u, 0u, 0u, 0u);
   uint32_t owner[APC_TILE_ITEMS];
 #pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j) owner[j] = slot[j] != VOX_NOSLOT ? slots[slot[j]].owner : 0u;
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {   // sector 0 = {key lo, key hi, first, cnt | owner, pad}: all loads in flight
+    head[j] = make_uint4(0u, 0u, 0u, 0u);
+    owner[j] = 0u;
+    if (slot[j] != VOX_NOSLOT) {
+      const uint4* raw = reinterpret_cast<const uint4*>(&slots[slot[j]]);
+      head[j] = raw[0];
+      owner[j] = raw[1].x;
+    }
+  }
   float4 cen[APC_TILE_ITEMS];
   uint32_t npts[APC_TILE_ITEMS];
   uint32_t gslot[APC_TILE_ITEMS], grank[APC_TILE_ITEMS];
@@ -132,8 +137,11 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
     if (is_first[j]) {
       const float4 po = pts[owner[j]];   // mostly i itself: 3 voxels in 4 hold one point
       const uint4* raw = reinterpret_cast<const uint4*>(&slots[slot[j]]);
-      const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
-      const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
+      ulonglong2 a01 = make_ulonglong2(0ull, 0ull), a23 = make_ulonglong2(0ull, 0ull);
+      if (head[j].w) {                   // sums exist only when somebody joined: sector 1 is not read otherwise
+        a01 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
+        a23 = *reinterpret_cast<const ulonglong2*>(&raw[3]);
+      }
       npts[j] = head[j].w + 1u;
       const double dc = (double)npts[j];
       cen[j] = make_float4(fixed_mean(a01.x + fixed_xyz(po.x), dc, 1.0 / 16777216.0),
@@ -163,12 +171,15 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
         grid.rank[r] = grank[j];
       }
       if (out_counts) out_counts[r] = npts[j];
-      rank_of_slot[s] = r;
-      // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0, acc = 0}
+      if (rank_of_slot) rank_of_slot[s] = r;   // only the point->voxel map needs it (a scattered 4-byte store per voxel)
+      // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0}; the sums only
+      // where they were written
       uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
       raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-      raw[1] = make_uint4(0u, 0u, 0u, 0u);
-      raw[2] = make_uint4(0u, 0u, 0u, 0u);
+      if (npts[j] > 1u) {
+        raw[2] = make_uint4(0u, 0u, 0u, 0u);
+        raw[3] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
   APC_STAMP(1, 3);
@@ -224,12 +235,12 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   APC_PROF(ctx, "k_voxel_finalize", s);
   if (radius_grid)
     k_voxel_finalize<true><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
-        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, *radius_grid);
   else
     k_voxel_finalize<false><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
-        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_rank,
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, GridDev{});
   APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
