@@ -20,25 +20,26 @@ enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
 
 #define APC_NUM_SCAN_STATES 8
 
-// One voxel of the open-addressing table.  Everything a point touches when it is inserted
-// (key CAS, first-index min, count, four fixed-point sums) sits in one aligned 64-byte
-// half-line = two 32-byte L2 sectors, instead of five lines of five separate arrays.
-// The point whose CAS claims the slot (the "owner") touches nothing else: it records its index
-// with a plain store and its coordinates are added when the voxel is finalised.  Only the points
-// that JOIN an existing voxel pay the six accumulating atomics - at 0.1 m on a 262k-point scan 77 %
-// of the voxels hold a single point, so a scan issues ~0.7 M atomics instead of 1.8 M (the insert
-// kernel is bound by the SM's ~1.3 cycles/lane issue rate for scattered atomics).
-struct __align__(64) VoxSlot {
-  // sector 0 (32 bytes): everything a single-point voxel ever touches
+// One voxel of the open-addressing table, split in two 32-byte halves kept in separate arrays.
+// VoxSlot ("hot") is everything a single-point voxel ever touches (77 % of the voxels of a 0.1 m C2
+// scan): the point whose CAS claims the slot (the "owner") records its index with a plain store and
+// its coordinates are added when the voxel is finalised.  Only the points that JOIN an existing voxel
+// pay the accumulating atomics (0.7 M per scan instead of 1.8 M), which land in VoxAcc ("cold").
+// Placement keeps neighbours together: the slot index is hash(2x2 block of voxels in x, y) * 4 + the
+// voxel's position inside the block, so the four slots of a 128-byte line (two 64-byte DRAM bursts)
+// belong to spatially adjacent voxels - a surface fills 2 to 4 of them instead of 1, which halves
+// the table's DRAM traffic (it is read and written back twice per scan, by insert and finalize).
+struct __align__(32) VoxSlot {
   unsigned long long key;     // packed 63-bit voxel key, all ones = empty
   uint32_t first;             // lowest index among the JOINING points (0xffffffff: none)
   uint32_t cnt;               // number of joining points (the owner is not counted)
   uint32_t owner;             // index of the point that claimed the slot
   uint32_t pad[3];
-  // sector 1: touched only when a second point joins the voxel (23 % of the voxels of a C2 scan)
+};
+struct __align__(32) VoxAcc {
   unsigned long long acc[4];  // fixed-point sums over the joining points: x, y, z (2^-24 m), intensity (2^-20)
 };
-static_assert(sizeof(VoxSlot) == 64, "VoxSlot must be one 64-byte half line");
+static_assert(sizeof(VoxSlot) == 32 && sizeof(VoxAcc) == 32, "voxel slots are one 32-byte sector each");
 
 // Optional per-kernel timing with CUDA events on the launching stream (apc_profile_*).
 struct ApcProf {
@@ -58,7 +59,8 @@ struct apc_ctx {
   uint32_t max_tiles = 0;
   // hash tables (capacity = power of two >= 2*max_points)
   uint32_t hash_cap = 0;
-  struct VoxSlot* vox_slots = nullptr;  // [hash_cap] 64-byte AoS slots {key, first, cnt, acc[4]}
+  struct VoxSlot* vox_slots = nullptr;  // [hash_cap] hot halves {key, first, cnt, owner}
+  struct VoxAcc* vox_acc = nullptr;     // [hash_cap] cold halves: fixed-point sums of the joining points
   uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
   uint32_t* p2slot = nullptr;       // [max_points]
   unsigned long long* dedup_slots = nullptr;  // [hash_cap] {key fingerprint:32 | lowest point index:32}

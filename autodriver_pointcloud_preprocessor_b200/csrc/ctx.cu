@@ -72,7 +72,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   apc_neighbors_release(ctx);
   apc_sort_release(ctx);
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
-  void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_rank, ctx->p2slot,
+  void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_acc, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_scores_copy, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
                   ctx->mask_a, ctx->idx_a, ctx->dev_counts};
@@ -112,6 +112,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   A(dalloc(&ctx->ctrl, 1));
   for (auto& p : ctx->scan_state) A(dalloc(&p, (size_t)ctx->max_tiles + 1024));   // + APC_SCAN_GROUPS group words
   A(dalloc(&ctx->vox_slots, C));
+  A(dalloc(&ctx->vox_acc, C));
   A(dalloc(&ctx->vox_rank, C));
   A(dalloc(&ctx->p2slot, M));
   A(dalloc(&ctx->dedup_slots, C));

@@ -2,7 +2,8 @@
 //
 // Replaces Open3D t.PointCloud.voxel_down_sample (pp.py:509-512).
 //   key       = floor(float32(x) / float32(voxel_size)) per axis, 21 bits each (+2^20 bias)
-//   table     = open addressing, linear probing, 64-bit atomicCAS on the key word
+//   table     = open addressing, 64-bit atomicCAS on the key word; 2x2 (x, y) blocks of voxels share
+//               a 128-byte line of four 32-byte slots, probing moves block by block (see VoxSlot)
 //   centroid  = order-independent fixed-point sums (rint(x*2^24), 64-bit integer atomics) so
 //               the result is deterministic and bit-identical to oracle/voxel.py
 //               centroids_fixed whatever order the atomics land in; the point that claims a
@@ -10,7 +11,7 @@
 //   order     = first-occurrence: a point is "first" when it holds the lowest index of its
 //               slot; an order-preserving scan over the first-flags numbers the voxels
 // The table is self-cleaning: the thread that finalises a voxel resets its slot, so no
-// per-frame memset of the (capacity x 52 B) table sits on the critical path.
+// per-frame memset of the (capacity x 64 B) table sits on the critical path.
 #include "apc_scan.cuh"
 #include "apc_grid.cuh"
 APC_TRACE_EXPORT(voxel)
@@ -44,7 +45,8 @@ __device__ __forceinline__ unsigned long long fixed_intensity(float w, ApcCtrl* 
 // resident warps to hide the dependent atomic chain).
 __global__ void __launch_bounds__(256)
 k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
-               VoxSlot* __restrict__ slots, uint32_t cap_mask, uint32_t* __restrict__ p2slot, ApcCtrl* ctrl) {
+               VoxSlot* __restrict__ slots, VoxAcc* __restrict__ accs, uint32_t cap_mask, uint32_t* __restrict__ p2slot,
+               ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t stride = gridDim.x * blockDim.x;
   APC_STAMP(0, 0);
@@ -56,10 +58,13 @@ k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
       p2slot[i] = VOX_NOSLOT;
       continue;
     }
-    uint32_t slot = (uint32_t)mix64(key) & cap_mask;
+    // block = the voxel's 2x2 neighbourhood in x, y (bit 0 of either index cleared); sub = its place in it
+    const uint64_t block = key & ~((1ull << 42) | (1ull << 21));
+    const uint32_t sub = (uint32_t)((key >> 42) & 1ull) | ((uint32_t)((key >> 21) & 1ull) << 1);
+    uint32_t slot = ((((uint32_t)mix64(block)) << 2) & cap_mask) | sub;
     unsigned long long old = atomicCAS(&slots[slot].key, VOX_EMPTY, (unsigned long long)key);
-    for (uint32_t probe = 1; old != VOX_EMPTY && old != key && probe <= cap_mask; ++probe) {  // linear probing
-      slot = (slot + 1) & cap_mask;
+    for (uint32_t probe = 1; old != VOX_EMPTY && old != key && probe <= (cap_mask >> 2); ++probe) {  // next block, same place
+      slot = (slot + 4) & cap_mask;
       old = atomicCAS(&slots[slot].key, VOX_EMPTY, (unsigned long long)key);
     }
     VoxSlot* s = &slots[slot];
@@ -70,10 +75,11 @@ k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
       p2slot[i] = slot;
       atomicMin(&s->first, i);
       atomicAdd(&s->cnt, 1u);
-      atomicAdd(&s->acc[0], fixed_xyz(p.x));
-      atomicAdd(&s->acc[1], fixed_xyz(p.y));
-      atomicAdd(&s->acc[2], fixed_xyz(p.z));
-      atomicAdd(&s->acc[3], fixed_intensity(p.w, ctrl));
+      VoxAcc* a = &accs[slot];
+      atomicAdd(&a->acc[0], fixed_xyz(p.x));
+      atomicAdd(&a->acc[1], fixed_xyz(p.y));
+      atomicAdd(&a->acc[2], fixed_xyz(p.z));
+      atomicAdd(&a->acc[3], fixed_intensity(p.w, ctrl));
     } else {
       atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
       p2slot[i] = VOX_NOSLOT;
@@ -97,7 +103,7 @@ __device__ __forceinline__ float fixed_mean(unsigned long long sum, double cnt, 
 template <bool GRID>
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, const uint32_t* __restrict__ p2slot,
-                 VoxSlot* __restrict__ slots, uint32_t* __restrict__ rank_of_slot,
+                 VoxSlot* __restrict__ slots, VoxAcc* __restrict__ accs, uint32_t* __restrict__ rank_of_slot,
                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
                  uint64_t* scan_state, ApcCtrl* ctrl, uint32_t n_tiles, const __grid_constant__ GridDev grid) {
   __shared__ uint32_t sm_scan[34];
@@ -136,11 +142,11 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
                   i == min(head[j].z, owner[j]);
     if (is_first[j]) {
       const float4 po = pts[owner[j]];   // mostly i itself: 3 voxels in 4 hold one point
-      const uint4* raw = reinterpret_cast<const uint4*>(&slots[slot[j]]);
       ulonglong2 a01 = make_ulonglong2(0ull, 0ull), a23 = make_ulonglong2(0ull, 0ull);
-      if (head[j].w) {                   // sums exist only when somebody joined: sector 1 is not read otherwise
-        a01 = *reinterpret_cast<const ulonglong2*>(&raw[2]);
-        a23 = *reinterpret_cast<const ulonglong2*>(&raw[3]);
+      if (head[j].w) {                   // sums exist only when somebody joined: the cold half is not read otherwise
+        const uint4* raw = reinterpret_cast<const uint4*>(&accs[slot[j]]);
+        a01 = *reinterpret_cast<const ulonglong2*>(&raw[0]);
+        a23 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
       }
       npts[j] = head[j].w + 1u;
       const double dc = (double)npts[j];
@@ -174,11 +180,11 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
       if (rank_of_slot) rank_of_slot[s] = r;   // only the point->voxel map needs it (a scattered 4-byte store per voxel)
       // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0}; the sums only
       // where they were written
-      uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
-      raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      *reinterpret_cast<uint4*>(&slots[s]) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
       if (npts[j] > 1u) {
-        raw[2] = make_uint4(0u, 0u, 0u, 0u);
-        raw[3] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* raw = reinterpret_cast<uint4*>(&accs[s]);
+        raw[0] = make_uint4(0u, 0u, 0u, 0u);
+        raw[1] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
@@ -195,18 +201,19 @@ __global__ void k_voxel_p2v(uint32_t n_max, const uint32_t* n_dev, const uint32_
 }
 
 // Whole-table reset (context creation and error recovery only).
-__global__ void k_voxel_reset(VoxSlot* slots, uint32_t cap) {
+__global__ void k_voxel_reset(VoxSlot* slots, VoxAcc* accs, uint32_t cap) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
     uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
     raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
     raw[1] = make_uint4(0u, 0u, 0u, 0u);
-    raw[2] = make_uint4(0u, 0u, 0u, 0u);
-    raw[3] = make_uint4(0u, 0u, 0u, 0u);
+    uint4* acc = reinterpret_cast<uint4*>(&accs[s]);
+    acc[0] = make_uint4(0u, 0u, 0u, 0u);
+    acc[1] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
 int apc_voxel_reset(apc_ctx* ctx, cudaStream_t s) {
-  k_voxel_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(ctx->vox_slots, ctx->hash_cap);
+  k_voxel_reset<<<APC_SM_COUNT * 4, 256, 0, s>>>(ctx->vox_slots, ctx->vox_acc, ctx->hash_cap);
   APC_LAUNCH_CHECK(ctx, "k_voxel_reset");
   return APC_OK;
 }
@@ -228,19 +235,19 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
     APC_PROF(ctx, "k_voxel_insert", s);
     const uint32_t ib = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
     k_voxel_insert<<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
-                                      ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
+                                      ctx->vox_acc, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
   }
   APC_LAUNCH_CHECK(ctx, "k_voxel_insert");
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_PROF(ctx, "k_voxel_finalize", s);
   if (radius_grid)
     k_voxel_finalize<true><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
-        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, out_p2v ? ctx->vox_rank : nullptr,
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_acc, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, *radius_grid);
   else
     k_voxel_finalize<false><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
-        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, out_p2v ? ctx->vox_rank : nullptr,
+        reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_acc, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, GridDev{});
   APC_LAUNCH_CHECK(ctx, "k_voxel_finalize");
