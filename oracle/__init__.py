@@ -17,6 +17,8 @@ reference file:line it follows):
   * ``voxel``    - Open3D >=0.18 ``voxel_down_sample`` (``pp.py:509-512``).
   * ``outliers`` - Open3D ``remove_statistical_outliers`` (``pp.py:514-519``) and
                    ``remove_radius_outliers`` (TODO at ``pp.py:37``).
+  * ``normals``  - Open3D ``estimate_normals`` hybrid search + analytic 3x3 eigen solver
+                   (``pp.py:521-530``).
   * ``ransac``   - Open3D legacy ``segment_plane`` (``pp.py:533-543``).
   * ``concat``   - ``pointcloud_concatenator.py:1-5`` (intent only; semantics defined here).
   * ``pipeline`` - ``pp.py:447-544`` ``preprocess`` stage order.
@@ -31,7 +33,7 @@ installable here, so:
     runs it on seeded inputs and commits the outputs under ``tests/golden/``; the oracle is
     checked against those vectors;
   * the stages delegated to Open3D / sensor_msgs_py (non-finite, transform, voxel, outliers,
-    RANSAC, read_points/create_cloud) are "PARITY UNPINNED": the oracle restates the
+    normals, RANSAC, read_points/create_cloud) are "PARITY UNPINNED": the oracle restates the
     published algorithm (Open3D v0.18/0.19 semantics) and *defines* the choices the
     reference leaves open (RANSAC hypothesis generator, voxel output order, reduction
     order).  Each such choice is written next to the function that makes it.
