@@ -2,6 +2,7 @@
 // statistical outliers -> radius outliers -> RANSAC ground removal, chained through device
 // counters so that no stage waits for the host, plus CUDA-graph capture / replay of the
 // whole chain (one launch per scan).
+#include <cmath>
 #include <cstdlib>
 
 #include "apc_grid.cuh"
@@ -86,7 +87,10 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   }
   if (has_stat) {
     float* out = dst();
-    const float hint = has_vox ? 2.0f * cfg->voxel_size : 0.0f;
+    // level-0 cell such that the k nearest of a point on a voxelised surface (one point per
+    // voxel_size^2: r_k = voxel_size * sqrt(k / pi)) usually lie inside the first 27-cell block; the
+    // result does not depend on it (the query climbs levels until the k-th distance is covered)
+    const float hint = has_vox ? cfg->voxel_size * fmaxf(2.0f, 1.3f * sqrtf((float)cfg->stat_nb_neighbors / 3.14159265f)) : 0.0f;
     rc = apc_statistical_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->stat_nb_neighbors, cfg->stat_std_ratio, hint,
                                  ctx->mask_a, nullptr, nullptr, s);
     if (rc) return rc;

@@ -146,4 +146,15 @@ def test_c5_batched_replay_matches_single_shot(big):
         for f in range(len(msgs)):
             n = int(carena[f, capi.CNT_OUTPUT])
             assert np.array_equal(arena[f, :n].cpu().numpy().view(np.uint32), want[f].view(np.uint32)), (rep, f)
+    # the multi-GPU path: graphs write the lanes' own buffers, every lane stages the frame's rows
+    # into the send slab right behind the graph
+    pipe.prepare_resident(pool, None, carena)
+    rows = max(w.shape[0] for w in want) + 7
+    slab = torch.zeros((len(msgs), rows, 4), device="cuda")
+    pipe.run_resident(list(range(len(msgs))), stage_to=slab)
+    torch.cuda.synchronize()
+    for f in range(len(msgs)):
+        n = int(carena[f, capi.CNT_OUTPUT])
+        assert n == want[f].shape[0]
+        assert np.array_equal(slab[f, :n].cpu().numpy().view(np.uint32), want[f].view(np.uint32)), f
     pipe.close()
