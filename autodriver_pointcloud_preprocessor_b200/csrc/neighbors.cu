@@ -230,16 +230,16 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
 struct TopK {
   float best[KNN_KMAX];
   uint32_t cnt;
+  float worst;   // best[k-1] once full, +inf before: candidates are rejected against a register
+  __device__ __forceinline__ void reset() { cnt = 0; worst = __int_as_float(0x7f800000); }
   __device__ __forceinline__ void push(float d2, uint32_t k) {
-    if (cnt < k) {
-      uint32_t j = cnt++;
-      while (j > 0 && best[j - 1] > d2) { best[j] = best[j - 1]; --j; }
-      best[j] = d2;
-    } else if (d2 < best[k - 1]) {
-      uint32_t j = k - 1;
-      while (j > 0 && best[j - 1] > d2) { best[j] = best[j - 1]; --j; }
-      best[j] = d2;
-    }
+    uint32_t j;
+    if (cnt < k) j = cnt++;
+    else if (d2 < worst) j = k - 1;
+    else return;
+    while (j > 0 && best[j - 1] > d2) { best[j] = best[j - 1]; --j; }
+    best[j] = d2;
+    if (cnt == k) worst = best[k - 1];
   }
   __device__ __forceinline__ float average(uint32_t k) const {  // sequential float32, ascending
     float s = sqrtf(best[0]);
@@ -276,7 +276,7 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
           }
       if (total < k_eff) continue;
       // pass 2: exact top-k over the block
-      tk.cnt = 0;
+      tk.reset();
       const float4* sp = g.sorted + (size_t)level * n_max;
       for (t = 0; t < 27; ++t)
         for (uint32_t u = cs[t]; u < ce[t]; ++u) {
@@ -308,7 +308,7 @@ k_knn_stragglers(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
     const uint32_t orig = stragglers[sidx];
     const float4 q = pts[orig];
     TopK tk;
-    tk.cnt = 0;
+    tk.reset();
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       const float4 p = pts[i];
       tk.push(d2_f32(q.x, q.y, q.z, p.x, p.y, p.z), k_eff);
