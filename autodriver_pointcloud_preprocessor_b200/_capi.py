@@ -48,6 +48,11 @@ class OutField(C.Structure):
                 ("attr_datatype", C.c_int32), ("attr_dev", C.c_void_p)]
 
 
+class PipelineMaps(C.Structure):
+    _fields_ = [("src_idx_dev", C.c_void_p), ("p2v_dev", C.c_void_p), ("voxel_counts_dev", C.c_void_p),
+                ("out_row_dev", C.c_void_p)]
+
+
 class PipelineCfg(C.Structure):
     _fields_ = [("filter", FilterCfg), ("voxel_size", C.c_float),
                 ("stat_enable", C.c_int32), ("stat_nb_neighbors", C.c_int32), ("stat_std_ratio", C.c_double),
@@ -90,6 +95,8 @@ def _load():
         "apc_segment_plane_scores": [vp, vp, u32, vp],
         "apc_repack": [vp, vp, u32, vp, C.POINTER(OutField), u32, u32, vp, vp],
         "apc_pipeline_run": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp, vp],
+        "apc_pipeline_run_maps": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
+                                  C.POINTER(PipelineMaps), vp],
         "apc_graph_capture_pipeline": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
                                        C.POINTER(vp)],
         "apc_graph_launch": [vp, vp, vp],
@@ -116,7 +123,7 @@ SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "
            "apc_ctx_max_points", "apc_frontend", "apc_unpack", "apc_transform", "apc_crop_mask",
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
-           "apc_statistical_outliers", "apc_estimate_normals", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run",
+           "apc_statistical_outliers", "apc_estimate_normals", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run", "apc_pipeline_run_maps",
            "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",
            "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report", "apc_pack_xyzi",
            "apc_split_xyzi"]

@@ -83,6 +83,7 @@ struct apc_ctx {
   float4* buf_b = nullptr;
   uint8_t* mask_a = nullptr;
   uint32_t* idx_a = nullptr;
+  uint32_t* idx_b = nullptr;        // second row-index buffer of the pipeline's index maps
   uint32_t* dev_counts = nullptr;   // [16] intermediate device counters
   // sorted-unique rows (sort.cu), allocated on first use
   uint4* sort_a = nullptr;          // [max_points] {kx, ky, kz, index} ping

@@ -23,6 +23,8 @@ struct GridDev {
   float4* sorted;            // [levels][n_max] xyz + original index (bits in w)
   float* cell;               // [levels] cell sizes (device)
   float cell0;               // > 0: single-level grid whose cell size the host knows (no k_grid_cells launch)
+  uint32_t cursor_base;      // first ctrl->counters slot of this grid's per-level scatter cursors (the radius
+                             // grid and the KNN grid can both be built inside one pipeline run)
 };
 __device__ __forceinline__ float grid_cell_size(const GridDev& g, uint32_t level) {
   return g.cell0 > 0.0f ? g.cell0 : g.cell[level];

@@ -75,7 +75,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_acc, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_scores_copy, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
-                  ctx->mask_a, ctx->idx_a, ctx->dev_counts};
+                  ctx->mask_a, ctx->idx_a, ctx->idx_b, ctx->dev_counts};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* p : ctx->scan_state)
@@ -133,6 +133,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   A(dalloc(&ctx->buf_b, M));
   A(dalloc(&ctx->mask_a, M));
   A(dalloc(&ctx->idx_a, M));
+  A(dalloc(&ctx->idx_b, M));
   A(dalloc(&ctx->dev_counts, 16));
   A(cudaMemset(ctx->ctrl, 0, sizeof(ApcCtrl)));
   for (auto& p : ctx->scan_state) A(cudaMemset(p, 0, ((size_t)ctx->max_tiles + 1024) * sizeof(uint64_t)));

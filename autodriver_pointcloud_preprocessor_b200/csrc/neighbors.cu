@@ -23,8 +23,9 @@ APC_TRACE_EXPORT(neighbors)
 #define KNN_KMAX 64
 
 // counters[] slots used by this file (zeroed by k_begin)
-#define CTR_CURSOR 0        // [0..KNN_LEVELS) per-level scatter cursors
+#define CTR_CURSOR 0        // [0..KNN_LEVELS) per-level scatter cursors of the KNN grid
 #define CTR_STRAGGLERS 12
+#define CTR_CURSOR_RADIUS 13  // scatter cursor of the single-level radius / normals grid
 #define CTR_BBOX 14         // 6 ordered-int floats: min xyz, max xyz
 
 // whole slot in one read-only 128-bit load (the table is not written while a query kernel runs)
@@ -125,7 +126,7 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&ctrl->counters[CTR_CURSOR + level], total);
+    if (lane == 31 && total) base = atomicAdd(&ctrl->counters[g.cursor_base + level], total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (cnt) g.slots[slot].start = base + incl - cnt;
   }
@@ -494,6 +495,7 @@ int apc_neighbors_prepare(apc_ctx* ctx, int which) {
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.cell, 16 * sizeof(float)));
   g.d.cap_mask = (uint32_t)cap - 1;
   g.d.levels = levels;
+  g.d.cursor_base = which == 0 ? CTR_CURSOR_RADIUS : CTR_CURSOR;
   g.cap = (uint32_t)cap;
   k_grid_reset<<<APC_SM_COUNT * 4, 256>>>(g.d.slots, (uint32_t)cap);
   APC_LAUNCH_CHECK(ctx, "k_grid_reset");
@@ -571,7 +573,7 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev, const uint8_t* __restrict__ mask,
                 GridDev g, float4* __restrict__ out, uint32_t* out_count, uint64_t* scan_state, const ApcCtrl* ctrl,
-                uint32_t n_tiles) {
+                uint32_t n_tiles, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ out_idx) {
   __shared__ uint32_t sm_scan[34];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
@@ -596,7 +598,13 @@ k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n
   const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
 #pragma unroll
   for (int j = 0; j < APC_TILE_ITEMS; ++j)
-    if (keep[j]) out[base + rank[j]] = v[j];
+    if (keep[j]) {
+      out[base + rank[j]] = v[j];
+      if (out_idx) {
+        const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+        out_idx[base + rank[j]] = idx_in ? idx_in[i] : i;
+      }
+    }
 }
 
 // radius outlier removal + select_by_mask for the pipeline: query, then the fused select/clean
@@ -614,7 +622,8 @@ int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
 
 int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_points,
                               double radius, uint8_t* mask_scratch, float* out_xyzi, uint32_t* out_count_dev,
-                              int scan_slot, int points_inserted, cudaStream_t s) {
+                              int scan_slot, int points_inserted, cudaStream_t s, const uint32_t* idx_in,
+                              uint32_t* out_idx) {
   APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
   if (n_max == 0) {
     APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
@@ -639,7 +648,8 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
   APC_PROF(ctx, "k_radius_select", s);
   k_radius_select<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, mask_scratch, g.d, reinterpret_cast<float4*>(out_xyzi),
-                                                       out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
+                                                       out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles,
+                                                       idx_in, out_idx);
   APC_LAUNCH_CHECK(ctx, "radius_select");
   return APC_OK;
 }

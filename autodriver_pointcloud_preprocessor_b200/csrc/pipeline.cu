@@ -15,13 +15,14 @@ int apc_voxel_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, float, 
                       int, const GridDev*, cudaStream_t);
 int apc_radius_grid_view(apc_ctx*, double, GridDev*);
 int apc_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, const uint8_t*, int, float*, uint32_t*,
-                       uint32_t*, int, cudaStream_t);
+                       uint32_t*, int, cudaStream_t, const uint32_t*);
 int apc_radius_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, float*, uint32_t*, int,
-                              int, cudaStream_t);
+                              int, cudaStream_t, const uint32_t*, uint32_t*);
 int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
-                              const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t);
+                              const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t,
+                              const uint32_t*, uint32_t*);
 int apc_neighbors_prepare(apc_ctx*, int);
 int apc_sort_prepare(apc_ctx*);
 
@@ -42,8 +43,14 @@ __global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t
   APC_STAMP(0, 0);
 }
 
+__global__ void k_iota(uint32_t* out, uint32_t n_max, const uint32_t* n_dev) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
 static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds, const apc_pipeline_cfg* cfg,
-                        float* out_xyzi, uint32_t* out_counts_dev, double* out_plane_dev, cudaStream_t s) {
+                        float* out_xyzi, uint32_t* out_counts_dev, double* out_plane_dev, cudaStream_t s,
+                        const apc_pipeline_maps* maps = nullptr) {
   APC_REQUIRE(ctx, clouds && cfg && out_xyzi && out_counts_dev, "NULL pointer");
   uint32_t n_total = 0;
   for (uint32_t i = 0; i < n_clouds && i < APC_MAX_CLOUDS; ++i) n_total += clouds[i].n_points;
@@ -64,9 +71,21 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     pong = d;
     return d;
   };
+  // index maps (apc_pipeline_run_maps): every selection after the voxel stage also carries, per
+  // surviving point, its row in the cloud the voxel stage produced; the last one writes out_row
+  uint32_t* const want_row = maps ? maps->out_row_dev : nullptr;
+  int sel_left = want_row ? has_stat + has_rad + has_ground : 0;
+  const uint32_t* row_in = nullptr;
+  uint32_t* row_bufs[2] = {ctx->idx_a, ctx->idx_b};
+  int row_flip = 0;
+  auto row_out = [&](void) -> uint32_t* {   // destination of the selection stage about to run
+    if (!want_row) return nullptr;
+    return --sel_left == 0 ? want_row : row_bufs[row_flip++ & 1];
+  };
   float* cur = dst();
   uint32_t cur_cnt = DC_FILTERED;
-  rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, nullptr, nullptr, dc + DC_FILTERED, 0, s);
+  rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, maps ? maps->src_idx_dev : nullptr, nullptr,
+                            dc + DC_FILTERED, 0, s);
   if (rc) return rc;
   // voxel -> radius with nothing in between: the voxel stage inserts its centroids into the radius
   // grid as it writes them (one launch and one pass over the centroids less)
@@ -79,8 +98,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
       rc = apc_radius_grid_view(ctx, cfg->radius_search_radius, &grid);
       if (rc) return rc;
     }
-    rc = apc_voxel_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->voxel_size, out, nullptr, nullptr, dc + DC_VOXELS, 1,
-                           grid_in_voxel ? &grid : nullptr, s);
+    rc = apc_voxel_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->voxel_size, out, maps ? maps->p2v_dev : nullptr,
+                           maps ? maps->voxel_counts_dev : nullptr, dc + DC_VOXELS, 1, grid_in_voxel ? &grid : nullptr, s);
     if (rc) return rc;
     cur = out;
     cur_cnt = DC_VOXELS;
@@ -94,31 +113,41 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     rc = apc_statistical_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->stat_nb_neighbors, cfg->stat_std_ratio, hint,
                                  ctx->mask_a, nullptr, nullptr, s);
     if (rc) return rc;
-    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, nullptr, dc + DC_STAT, 2, s);
+    uint32_t* rows = row_out();
+    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, rows, dc + DC_STAT, 2, s, row_in);
     if (rc) return rc;
+    row_in = rows;
     cur = out;
     cur_cnt = DC_STAT;
   }
   if (has_rad) {
     float* out = dst();
     // the select_by_mask of the radius decision also cleans the neighbour grid (one launch)
+    uint32_t* rows = row_out();
     rc = apc_radius_select_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
-                                   ctx->mask_a, out, dc + DC_RADIUS, 3, grid_in_voxel ? 1 : 0, s);
+                                   ctx->mask_a, out, dc + DC_RADIUS, 3, grid_in_voxel ? 1 : 0, s, row_in, rows);
     if (rc) return rc;
+    row_in = rows;
     cur = out;
     cur_cnt = DC_RADIUS;
   }
   if (has_ground) {
     float* out = dst();
     double* plane = out_plane_dev ? out_plane_dev : ctx->red_b;
+    uint32_t* rows = row_out();
     // pp.py:542 select_by_index(inliers, invert=True) is fused into the final RANSAC pass: the
     // non-ground points are written in order straight to `out`
     rc = apc_segment_plane_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->ground_distance_threshold, cfg->ground_ransac_n,
                                    cfg->ground_num_iterations, cfg->ground_probability, cfg->ground_seed, nullptr, plane,
-                                   nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s);
+                                   nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s, row_in, rows);
     if (rc) return rc;
+    row_in = rows;
     cur = out;
     cur_cnt = DC_OUT;
+  }
+  if (want_row && !row_in && n_total) {   // no selection stage ran: output row i is row i
+    k_iota<<<min(apc_div_up(n_total, 256), (uint32_t)APC_SM_COUNT * 4), 256, 0, s>>>(want_row, n_total, dc + cur_cnt);
+    APC_LAUNCH_CHECK(ctx, "k_iota");
   }
   k_pipeline_counts<<<1, 1, 0, s>>>(dc, n_total, cur_cnt, has_vox, has_stat, has_rad, has_ground, ctx->ctrl, out_counts_dev);
   APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
@@ -141,6 +170,16 @@ extern "C" int apc_pipeline_run(apc_ctx* ctx, const apc_cloud_desc* clouds, uint
   int rc = prepare(ctx, cfg);
   if (rc) return rc;
   return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream);
+}
+
+extern "C" int apc_pipeline_run_maps(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                     const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                     double* out_plane_dev, const apc_pipeline_maps* maps, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, cfg && maps, "NULL pointer");
+  int rc = prepare(ctx, cfg);
+  if (rc) return rc;
+  return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream, maps);
 }
 
 struct apc_graph {

@@ -496,7 +496,8 @@ __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes_in,
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, double* __restrict__ plane8,
            uint32_t* __restrict__ info, double thr, uint8_t* __restrict__ mask, double* __restrict__ partials,
-           float4* __restrict__ keep_out, uint32_t* keep_count, uint64_t* scan_state, uint32_t n_tiles, ApcCtrl* ctrl) {
+           float4* __restrict__ keep_out, uint32_t* keep_count, uint64_t* scan_state, uint32_t n_tiles, ApcCtrl* ctrl,
+           const uint32_t* __restrict__ keep_idx_in, uint32_t* __restrict__ keep_idx_out) {
   __shared__ double s_red[8][10];
   __shared__ bool s_last;
   __shared__ uint32_t sm_scan[34];
@@ -534,7 +535,13 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     const uint32_t base = tile_compact_offsets(keep, rank, sm_scan, scan_state, blockIdx.x, ctrl->epoch, keep_count, n_tiles);
 #pragma unroll
     for (int j = 0; j < APC_TILE_ITEMS; ++j)
-      if (keep[j]) keep_out[base + rank[j]] = p[j];
+      if (keep[j]) {
+        keep_out[base + rank[j]] = p[j];
+        if (keep_idx_out) {
+          const uint32_t i = blockIdx.x * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+          keep_idx_out[base + rank[j]] = keep_idx_in ? keep_idx_in[i] : i;
+        }
+      }
   }
   // tiles past the device-side count hold no points: no partial row (the last CTA reads only the
   // rows of the tiles in use - adding their zeros would not change a bit of the sums)
@@ -589,7 +596,8 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
 int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, double thr,
                               int ransac_n, int iters, double prob, uint64_t seed, const int32_t* table,
                               double* out_plane, uint8_t* out_mask, uint32_t* out_info, float* out_keep_xyzi,
-                              uint32_t* out_keep_count, int scan_slot, cudaStream_t s) {
+                              uint32_t* out_keep_count, int scan_slot, cudaStream_t s, const uint32_t* keep_idx_in,
+                              uint32_t* keep_idx_out) {
   APC_REQUIRE(ctx, out_plane && out_info && (out_mask || out_keep_xyzi), "NULL output pointer");
   APC_REQUIRE(ctx, !out_keep_xyzi || out_keep_count, "out_keep_count is NULL");
   APC_REQUIRE(ctx, prob > 0.0 && prob <= 1.0, "probability must be in (0, 1]");
@@ -634,7 +642,7 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   APC_PROF(ctx, "k_rs_final", s);
   k_rs_final<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials,
                                                   reinterpret_cast<float4*>(out_keep_xyzi), out_keep_count,
-                                                  ctx->scan_state[scan_slot], n_tiles, ctx->ctrl);
+                                                  ctx->scan_state[scan_slot], n_tiles, ctx->ctrl, keep_idx_in, keep_idx_out);
   APC_LAUNCH_CHECK(ctx, "segment_plane");
   return APC_OK;
 }
@@ -650,7 +658,7 @@ extern "C" int apc_segment_plane(apc_ctx* ctx, const float* xyzi, uint32_t n_max
   if (rc) return rc;
   return apc_segment_plane_nobegin(ctx, xyzi, n_max, n_dev, distance_threshold, ransac_n, num_iterations, probability,
                                    seed, sample_table_dev, out_plane_dev, out_inlier_mask, out_info_dev, nullptr, nullptr,
-                                   4, s);
+                                   4, s, nullptr, nullptr);
 }
 
 // Per-hypothesis tallies {inlier count, integer error sum} of the most recent segment_plane call.

@@ -71,6 +71,7 @@ def make_cloud_desc(fields, point_step: int, n_points: int, data_dev: torch.Tens
         T = np.asarray(transform, dtype=np.float32).reshape(16)
         for i in range(16):
             d.transform[i] = float(T[i])
+    d._keep_alive = data_dev            # the struct holds a raw device pointer: keep the tensor alive with it
     return d
 
 
@@ -338,6 +339,23 @@ class Context:
         self._ok(lib.apc_pipeline_run(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi), _ptr(out_counts),
                                       _ptr(out_plane), _stream()))
         return out_xyzi, out_counts, out_plane
+
+    def pipeline_run_maps(self, clouds, pcfg: PipelineCfg):
+        """preprocess() plus the index maps that let the caller carry any other attribute through it
+        (``apc_pipeline_run_maps``).  Returns ``(out_xyzi, counts, plane, maps)`` with ``maps`` a dict
+        of device tensors ``src_idx`` / ``p2v`` / ``voxel_counts`` / ``out_row`` (int32, full size;
+        valid lengths are in ``counts``)."""
+        n_total = sum(c.n_points for c in clouds)
+        arr = (CloudDesc * len(clouds))(*clouds)
+        out_xyzi = self._empty((max(n_total, 1), 4), torch.float32)
+        out_counts = torch.zeros((8,), dtype=torch.int32, device=self.device)
+        out_plane = torch.zeros((8,), dtype=torch.float64, device=self.device)
+        maps = {k: self._empty((max(n_total, 1),), torch.int32) for k in ("src_idx", "p2v", "voxel_counts", "out_row")}
+        m = _capi.PipelineMaps(maps["src_idx"].data_ptr(), maps["p2v"].data_ptr(), maps["voxel_counts"].data_ptr(),
+                               maps["out_row"].data_ptr())
+        self._ok(lib.apc_pipeline_run_maps(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi), _ptr(out_counts),
+                                           _ptr(out_plane), C.byref(m), _stream()))
+        return out_xyzi, out_counts, out_plane, maps
 
     def capture_pipeline(self, clouds, pcfg: PipelineCfg, out_xyzi, out_counts, out_plane):
         """Capture the pipeline over fixed buffers into a CUDA graph; returns a handle for

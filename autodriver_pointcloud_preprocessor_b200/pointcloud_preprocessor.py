@@ -50,7 +50,7 @@ from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, Extrapolation
                           LookupException, Node, Parameter, ParameterDescriptor, ParameterType, PointCloud2,
                           PointField, QoSHistoryPolicy, QoSProfile, QoSReliabilityPolicy, SetParametersResult,
                           TransformListener, point_cloud2, rclpy, tf2_ros)
-from .utils import (FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
+from .utils import (raw_column, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
                     convert_pointcloud_to_numpy, crop_pointcloud, dict_to_open3d_tensor_pointcloud,
                     extract_rgb_from_pointcloud, get_current_time, get_fields_from_dicts, get_pointcloud_metadata,
                     get_time_difference, numpy_struct_to_pointcloud2, pointcloud_to_dict, remove_duplicates,
@@ -294,8 +294,10 @@ class PointcloudPreprocessorNode(Node):
             return True
         if self.fused_pipeline is False or str(self.fused_pipeline).lower() in ('false', '0', 'off'):
             return False
+        # 'auto': the fused pipeline carries x, y, z, intensity itself and ring / time / return_type
+        # through its index maps; colour clouds take the staged carrier path
         m = self.pointcloud_metadata or {}
-        return not (m.get('has_ring') or m.get('has_time') or m.get('has_return_type') or m.get('has_rgb'))
+        return not m.get('has_rgb')
 
     # ------------------------------------------------------------------------------------------------
     def extract_pointcloud(self, ros_cloud):
@@ -411,7 +413,13 @@ class PointcloudPreprocessorNode(Node):
                         ransac_n=self.remove_ground_ransac_number, num_iterations=self.remove_ground_num_iterations,
                         probability=self.remove_ground_probability, seed=self.remove_ground_seed)
             if (self.remove_ground and not self.estimate_normals) else None)
-        out, counts, plane = ctx.pipeline_run([desc], pcfg)
+        meta = self.pointcloud_metadata
+        extra = [k for k in ('ring', 'time', 'return_type') if meta.get(f'has_{k}')]
+        maps = None
+        if extra:
+            out, counts, plane, maps = ctx.pipeline_run_maps([desc], pcfg)
+        else:
+            out, counts, plane = ctx.pipeline_run([desc], pcfg)
         ctx.check()
         c = counts.cpu().numpy()
         n_out = int(c[_capi.CNT_OUTPUT])
@@ -420,6 +428,23 @@ class PointcloudPreprocessorNode(Node):
         cloud.point['positions'] = pos if self.use_gpu else pos.cpu()
         if inten is not None:
             cloud.point['intensity'] = (inten if self.use_gpu else inten.cpu()).reshape(-1, 1)
+        if maps is not None:
+            # attributes the kernels do not touch: cut from the message bytes, gathered with the front
+            # end's surviving indices, averaged per voxel "in float32 then cast back" like Open3D does
+            # for every attribute (pp.py:511), gathered with the rows that survived the later stages
+            m_filt, n_vox = int(c[_capi.CNT_FILTERED]), int(c[_capi.CNT_VOXELS])
+            rows = raw[:n * msg.point_step].view(n, msg.point_step)
+            by_name = {f.name: f for f in msg.fields}
+            ref_dtype = {'ring': torch.uint16, 'time': torch.float64, 'return_type': torch.uint8}   # utils.py:120-131
+            for key in extra:
+                col = raw_column(rows, by_name[meta[f'{key}_field_name']]).to(ref_dtype[key])
+                a = ctx.gather(col, maps['src_idx'], m_filt)
+                if self.voxel_size > 0.0:
+                    mean = ctx.voxel_mean_attr(a.to(torch.float32).contiguous(), maps['p2v'],
+                                               counts[_capi.CNT_VOXELS:_capi.CNT_VOXELS + 1], m_filt)[:n_vox]
+                    a = mean.to(ref_dtype[key])
+                a = ctx.gather(a.contiguous(), maps['out_row'], n_out)
+                cloud.point[key] = (a if self.use_gpu else a.cpu()).reshape(-1, 1)
         self.o3d_pointcloud = cloud
         self._fused_xyzi = (out[:n_out], cloud)       # prepare_pointcloud repacks straight from this
         self.last_counts = c

@@ -122,6 +122,14 @@ def numpy_struct_to_pointcloud2(field_names: list,
     return fields, offset
 
 
+def raw_column(rows, field):
+    """One field of every record of a device byte buffer viewed as ``[n, point_step]``: a contiguous
+    device tensor of the field's own dtype (the per-field slice ``read_points`` returns)."""
+    np_dt = np.dtype(FIELD_DTYPE_MAP[field.datatype])
+    col = rows[:, field.offset:field.offset + np_dt.itemsize].contiguous().view(getattr(torch, _TORCH_OF[np_dt]))
+    return col.reshape(-1)
+
+
 def pointcloud_to_dict(ros_cloud, field_names=None, skip_nans=True, organize_cloud=False, metadata_dict=None,
                        _data_dev=None):
     """utils.py:202-223, with ``read_points`` + ``convert_pointcloud_to_numpy`` executed on the GPU.
@@ -170,10 +178,7 @@ def pointcloud_to_dict(ros_cloud, field_names=None, skip_nans=True, organize_clo
     rows = data[:n * ros_cloud.point_step].view(n, ros_cloud.point_step) if n else None
 
     def column(name, np_dtype):
-        f = by_name[name]
-        size = np.dtype(FIELD_DTYPE_MAP[f.datatype]).itemsize
-        col = rows[:, f.offset:f.offset + size].contiguous().view(getattr(torch, _TORCH_OF[np.dtype(FIELD_DTYPE_MAP[f.datatype])]))
-        return ctx.gather(col.reshape(-1), src, m).to(getattr(torch, _TORCH_OF[np.dtype(np_dtype)]))
+        return ctx.gather(raw_column(rows, by_name[name]), src, m).to(getattr(torch, _TORCH_OF[np.dtype(np_dtype)]))
 
     for key, np_dtype in (('ring', np.uint16), ('time', np.float64), ('return_type', np.uint8)):
         if metadata_dict.get(f'has_{key}') and n:

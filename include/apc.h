@@ -303,6 +303,25 @@ int apc_pipeline_run(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clou
                      const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
                      double* out_plane_dev, void* stream);
 
+/* Index maps of one pipeline run, for carrying attributes the kernels do not touch (ring, time,
+ * return_type, rgb, any extra field: pp.py:593-618 copy_fields) through the fused pipeline: gather
+ * by src_idx, average per voxel with apc_voxel_mean_attr (p2v, voxel_counts), gather by out_row.
+ * Every pointer is a device array of sum(n_points) elements and may be NULL.
+ *   src_idx_dev       uint32: input index of every point that left the front end
+ *   p2v_dev           int32:  voxel row of every such point (voxel stage enabled)
+ *   voxel_counts_dev  uint32: points per voxel row
+ *   out_row_dev       uint32: for every output point, its row in the cloud after the voxel stage
+ *                             (after the front end when the voxel stage is off) */
+typedef struct apc_pipeline_maps {
+  uint32_t* src_idx_dev;
+  int32_t* p2v_dev;
+  uint32_t* voxel_counts_dev;
+  uint32_t* out_row_dev;
+} apc_pipeline_maps;
+int apc_pipeline_run_maps(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                          const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                          double* out_plane_dev, const apc_pipeline_maps* maps, void* stream);
+
 /* The same pipeline captured once into a CUDA graph (fixed buffers, sizes and config) and
  * replayed per scan: one launch per frame instead of ~25.  The per-frame input is whatever
  * the captured data_dev buffers hold when apc_graph_launch runs. */

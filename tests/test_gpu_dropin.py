@@ -146,12 +146,8 @@ def test_node_callback_end_to_end(layout, fused):
     got = np.stack([arr["x"], arr["y"], arr["z"]], 1)
     assert np.array_equal(got.view(np.uint32), ref["positions"].view(np.uint32))
     assert np.array_equal(arr["intensity"].view(np.uint32), ref["intensity"].view(np.uint32))
-    uses_fused = fused == "true" or (fused == "auto" and layout == "xyzi16")
     if "ring" in arr.dtype.names:
-        if uses_fused:
-            assert not arr["ring"].any()            # fused path carries xyz + intensity only (documented)
-        else:
-            assert arr["ring"].any()                # staged path carries / averages every known attribute
+        assert arr["ring"].any()                    # both paths carry / voxel-average every known attribute
     assert set(node.processing_times) >= {"ros_to_numpy", "preprocessing_time", "pointcloud_msg_parsing",
                                           "pointcloud_pub", "total_callback_time", "tf_lookup"}
     assert out.is_dense == (msg.is_dense and True)
@@ -231,3 +227,29 @@ def test_node_callback_with_normals_and_reference_backends(layout, fused, backen
     close = np.abs(nrm - ref["normals"]).max(axis=1) < 1e-5                     # float tolerance: 1e-5 per component
     assert close.mean() > 0.98                                                  # the rest: near-degenerate neighbourhoods
     assert "normal_estimation" in node.processing_times
+
+
+def test_fused_and_staged_paths_publish_the_same_cloud():
+    """Velodyne-style layout (x, y, z, intensity, ring u16, time f32): the fused pipeline (attributes
+    carried through its index maps) and the staged carrier path publish the same message - positions
+    and intensity bit-equal; ring / time are float32 voxel means accumulated with atomics in both
+    paths, so they agree to the last float32 bit or so (ring within 1 after the cast back)."""
+    from oracle import pc2
+    scan, msg = scan_msg("xyzirt22", seed=49, n_beams=32, n_az=1024)
+    outs = {}
+    for fused in ("true", "false"):
+        node = make_node({"use_gpu": True, "voxel_size": 0.1, "remove_ground": True, "remove_ground.seed": 3,
+                          "remove_radius_outliers": True, "estimate_normals": False, "fused_pipeline": fused})
+        node.callback(msg)
+        assert len(node.pointcloud_pub.messages) == 1, "callback dropped the frame"
+        out = node.pointcloud_pub.messages[0]
+        outs[fused] = np.frombuffer(out.data, dtype=pc2.dtype_from_fields(out.fields, out.point_step))
+    a, b = outs["true"], outs["false"]
+    assert a.shape == b.shape and a.dtype == b.dtype
+    for k in ("x", "y", "z", "intensity"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert a["ring"].any() and np.max(np.abs(a["ring"].astype(np.int64) - b["ring"].astype(np.int64))) <= 1
+    assert np.allclose(a["time"], b["time"], rtol=1e-5, atol=1e-7)
+    # single-point voxels carry the input's attribute values exactly: most of the cloud at 0.1 m
+    exact = (a["ring"] == b["ring"]).mean()
+    assert exact > 0.95

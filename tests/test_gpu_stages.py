@@ -362,6 +362,9 @@ PIPE_CASES = {
                ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=7)),
     "C4": dict(voxel_size=0.05, statistical=dict(nb_neighbors=20, std_ratio=2.0)),
     "crop_only": dict(voxel_size=0.0),
+    # both neighbour grids (KNN levels + radius cells) built inside one run
+    "all": dict(voxel_size=0.1, statistical=dict(nb_neighbors=8, std_ratio=1.5), radius=dict(nb_points=4, radius=0.4),
+                ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=50, probability=0.99, seed=5)),
 }
 
 
@@ -405,3 +408,48 @@ def test_pipeline_parity(env, case, graph):
     if stages.get("ground"):
         assert int(c[capi.CNT_GROUND_INLIERS]) == ref["ground_inliers"].size
         assert np.allclose(plane.cpu().numpy()[:4], ref["plane"], rtol=0, atol=1e-5)
+
+
+def test_pipeline_index_maps(env):
+    """apc_pipeline_run_maps: src_idx / p2v / voxel_counts / out_row against the oracle pipeline's
+    intermediates (index work: bit-exact), with and without selection stages after the voxel stage."""
+    from oracle import pipeline as opipe
+    ctx, engine, synth, capi = env["ctx"], env["engine"], env["synth"], env["capi"]
+    msg = synth.pack_cloud(small_scan(synth, seed=37, n_beams=32, n_az=1024), "xyzirt22")
+    data = dev_bytes(msg)                                   # keep the device buffer alive: desc holds a raw pointer
+    desc = engine.make_cloud_desc(msg.fields, msg.point_step, msg.width, data)
+    crop = dict(min=[-60.0, -60.0, -20.0], max=[60.0, 60.0, 20.0], invert=False, mode=capi.CROP_OPEN3D)
+    fcfg = engine.make_filter_cfg(skip_nans=True, dedup_mode=capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True,
+                                  transforms=[T_A], crop=crop)
+    cases = [dict(voxel_size=0.1),
+             dict(voxel_size=0.1, radius=dict(nb_points=4, radius=0.4)),
+             dict(voxel_size=0.1, statistical=dict(nb_neighbors=8, std_ratio=1.5), radius=dict(nb_points=4, radius=0.4),
+                  ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=50, probability=0.99, seed=5)),
+             dict(ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=50, probability=0.99, seed=5))]
+    for stages in cases:
+        out, counts, plane, maps = ctx.pipeline_run_maps([desc], engine.make_pipeline_cfg(fcfg, **stages))
+        ctx.check()
+        cfg = opipe.default_config()
+        cfg.update(transforms=[T_A], crop=crop, voxel_size=stages.get("voxel_size", 0.0), statistical=stages.get("statistical"),
+                   radius=stages.get("radius"), ground=stages.get("ground"))
+        ref = opipe.preprocess(msg, cfg)
+        c = counts.cpu().numpy()
+        m, n_out = int(c[capi.CNT_FILTERED]), int(c[capi.CNT_OUTPUT])
+        assert np.array_equal(maps["src_idx"][:m].cpu().numpy().astype(np.uint32), ref["src_idx"])
+        rows = np.arange(m)
+        if stages.get("voxel_size"):
+            v = int(c[capi.CNT_VOXELS])
+            assert np.array_equal(maps["p2v"][:m].cpu().numpy(), ref["p2v"])
+            assert np.array_equal(maps["voxel_counts"][:v].cpu().numpy(), ref["voxel_counts"])
+            rows = np.arange(v)
+        if stages.get("statistical"):
+            rows = rows[ref["statistical_mask"]]
+        if stages.get("radius"):
+            rows = rows[ref["radius_mask"]]
+        if stages.get("ground"):
+            keep = np.ones(rows.shape[0], dtype=bool)
+            keep[ref["ground_inliers"]] = False
+            rows = rows[keep]
+        assert n_out == rows.shape[0] == ref["positions"].shape[0]
+        assert np.array_equal(maps["out_row"][:n_out].cpu().numpy(), rows)
+        assert np.array_equal(out[:n_out, :3].cpu().numpy().view(np.uint32), ref["positions"].view(np.uint32))
