@@ -453,3 +453,66 @@ def test_pipeline_index_maps(env):
         assert n_out == rows.shape[0] == ref["positions"].shape[0]
         assert np.array_equal(maps["out_row"][:n_out].cpu().numpy(), rows)
         assert np.array_equal(out[:n_out, :3].cpu().numpy().view(np.uint32), ref["positions"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_pipeline_random_stage_combinations(env, seed):
+    """Seeded random combinations of layouts, duplicate-removal back ends, crop modes, transforms and
+    stages (the stages share scratch: tables, scan states, counters, cursors) against the oracle
+    pipeline, eager and replayed; everything bit-exact except the refit plane (1e-5)."""
+    from oracle import dedup as odedup
+    from oracle import pipeline as opipe
+    ctx, engine, synth, capi = env["ctx"], env["engine"], env["synth"], env["capi"]
+    rng = np.random.default_rng(1000 + seed)
+    layout = ["xyzi16", "xyzirt22", "ouster48"][rng.integers(3)]
+    scan = small_scan(synth, seed=200 + seed, n_beams=int(rng.choice([16, 32])), n_az=int(rng.choice([256, 512, 1024])))
+    msg = synth.pack_cloud(scan, layout, is_dense=bool(rng.integers(2)) and False)
+    data = dev_bytes(msg)
+    desc = engine.make_cloud_desc(msg.fields, msg.point_step, msg.width, data)
+    dedup = int(rng.choice([capi.DEDUP_OFF, capi.DEDUP_OPEN3D, capi.DEDUP_NUMPY, capi.DEDUP_TORCH_COMPAT]))
+    crop = None
+    if rng.integers(4):
+        crop = dict(min=[-40.0, -35.5, -2.5], max=[38.0, 44.0, 6.0], invert=bool(rng.integers(4) == 0), mode=int(rng.integers(3)))
+    transforms = [T_A, T_B][:int(rng.integers(3))]
+    stages = {}
+    if rng.integers(4):
+        stages["voxel_size"] = float(rng.choice([0.1, 0.25, 0.5]))
+    if rng.integers(2):
+        stages["statistical"] = dict(nb_neighbors=int(rng.choice([4, 10, 20])), std_ratio=float(rng.choice([1.0, 2.0])))
+    if rng.integers(2):
+        stages["radius"] = dict(nb_points=int(rng.choice([2, 5])), radius=float(rng.choice([0.3, 0.6, 1.2])))
+    if rng.integers(2):
+        stages["ground"] = dict(distance_threshold=0.2, ransac_n=int(rng.choice([3, 5])), num_iterations=int(rng.choice([30, 100])),
+                                probability=0.99, seed=int(rng.integers(100)))
+    fcfg = engine.make_filter_cfg(skip_nans=True, dedup_mode=dedup, remove_nan=True, remove_inf=True,
+                                  transforms=transforms, crop=crop)
+    pcfg = engine.make_pipeline_cfg(fcfg, **stages)
+    cfg = opipe.default_config()
+    cfg.update(dedup_mode={capi.DEDUP_OFF: odedup.DEDUP_OFF, capi.DEDUP_OPEN3D: odedup.DEDUP_OPEN3D,
+                           capi.DEDUP_NUMPY: odedup.DEDUP_NUMPY, capi.DEDUP_TORCH_COMPAT: odedup.DEDUP_TORCH_COMPAT}[dedup],
+               transforms=transforms, crop=crop, voxel_size=stages.get("voxel_size", 0.0),
+               statistical=stages.get("statistical"), radius=stages.get("radius"), ground=stages.get("ground"))
+    ref = opipe.preprocess(msg, cfg)
+    out = torch.zeros((msg.width, 4), device="cuda")
+    counts = torch.zeros(8, dtype=torch.int32, device="cuda")
+    plane = torch.zeros(8, dtype=torch.float64, device="cuda")
+    what = (layout, dedup, crop, len(transforms), stages)
+    for mode in ("eager", "graph"):
+        out.zero_(); counts.zero_()
+        if mode == "graph":
+            g = ctx.capture_pipeline([desc], pcfg, out, counts, plane)
+            out.zero_(); counts.zero_()
+            ctx.launch_graph(g)
+            ctx.launch_graph(g)
+        else:
+            ctx.pipeline_run([desc], pcfg, out, counts, plane)
+        ctx.check()
+        c = counts.cpu().numpy()
+        assert c[capi.CNT_STATUS] == 0 and c[capi.CNT_FILTERED] == ref["n_filtered"], what
+        n_out = int(c[capi.CNT_OUTPUT])
+        assert n_out == ref["positions"].shape[0], (mode, what)
+        got = out[:n_out].cpu().numpy()
+        assert same_f32(got[:, :3], ref["positions"]), (mode, what)
+        assert same_f32(got[:, 3], ref["intensity"]), (mode, what)
+        if stages.get("ground") and ref["ground_inliers"].size >= 3:
+            assert np.allclose(plane.cpu().numpy()[:4], ref["plane"], rtol=0, atol=1e-5), (mode, what)
