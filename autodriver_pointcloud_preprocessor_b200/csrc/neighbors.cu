@@ -126,7 +126,10 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&ctrl->counters[g.cursor_base + level], total);
+    if (lane == 31 && total) {
+      base = atomicAdd(&ctrl->counters[g.cursor_base + level], total);
+      if (base + total > n_max) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);   // cursor not reset / corrupt table: never scatter past the array
+    }
     base = __shfl_sync(0xffffffffu, base, 31);
     if (cnt) g.slots[slot].start = base + incl - cnt;
   }
@@ -142,8 +145,8 @@ k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
     const uint32_t slot = g.slot[(size_t)level * n_max + i];
     if (slot == GRID_NOSLOT) continue;
     const float4 p = pts[i];
-    g.sorted[(size_t)level * n_max + g.slots[slot].start + g.rank[(size_t)level * n_max + i]] =
-        make_float4(p.x, p.y, p.z, __uint_as_float(i));
+    const uint32_t pos = g.slots[slot].start + g.rank[(size_t)level * n_max + i];
+    if (pos < n_max) g.sorted[(size_t)level * n_max + pos] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
   }
   APC_STAMP(3, 1);
 }
