@@ -252,47 +252,140 @@ struct TopK {
   }
 };
 
-__global__ void __launch_bounds__(128)
+// One WARP per query (the per-thread version - a sorted list in local memory - ran at 7 active lanes
+// per instruction and 1750 warp instructions per query: profiles, prof_c4).  Per level:
+//   1. lanes 0..26 resolve the 27 neighbour cells in parallel; a warp scan of the run lengths gives
+//      the flat candidate list and tells whether the block holds k points at all;
+//   2. the lanes stride over the flat list (run found by a 5-step shuffle search), compute the
+//      float32 distances and drop their bit patterns (non-negative floats order like integers)
+//      into the warp's shared buffer; longer lists go through the buffer in chunks, each chunk
+//      merged with the k best so far;
+//   3. the k-th smallest value is found by a 31-step binary search on the bit pattern (each step a
+//      strided count + REDUX), the k smallest are compacted in place (ties at the k-th value are
+//      interchangeable);
+//   4. the level's answer stands if the k-th distance is covered by the block (same test as before);
+//      then the k values are rank-sorted and summed in ascending order by shuffles - the same
+//      sequential float32 sum as oracle/outliers.py.
+#define KNN_CAP 1024
+#define KNN_WARPS 4
+__global__ void __launch_bounds__(KNN_WARPS * 32)
 k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float* __restrict__ avg,
             uint32_t* __restrict__ stragglers, ApcCtrl* ctrl) {
+  __shared__ uint32_t s_buf[KNN_WARPS][KNN_CAP];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t k_eff = min(k, n);
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* buf = s_buf[w];
+  uint32_t* sorted_k = buf + KNN_CAP / 2;          // free once the k best sit at the front (k <= 64)
+  for (uint32_t j = blockIdx.x * KNN_WARPS + w; j < n; j += gridDim.x * KNN_WARPS) {
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
     bool done = false;
-    TopK tk;
     for (uint32_t level = 0; level < g.levels && !done; ++level) {
       const float c = g.cell[level];
       int32_t ix, iy, iz;
       if (!grid_coord(q.x, q.y, q.z, c, ix, iy, iz)) continue;
-      // pass 1: are there at least k points in the 27-cell block at all?
-      uint32_t cs[27], ce[27], total = 0;
-      int t = 0;
-      for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-          for (int dx = -1; dx <= 1; ++dx, ++t) {
-            uint32_t b, f;
-            if (!grid_lookup(g, grid_key(level, ix + dx, iy + dy, iz + dz), b, f)) { cs[t] = ce[t] = 0; continue; }
-            cs[t] = b;
-            ce[t] = b + f;
-            total += f;
-          }
+      // 1. the 27 cells, one per lane
+      uint32_t cs = 0, cf = 0;
+      if (lane < 27) {
+        const int dx = (int)(lane % 3u) - 1, dy = (int)((lane / 3u) % 3u) - 1, dz = (int)(lane / 9u) - 1;
+        uint32_t b, f;
+        if (grid_lookup(g, grid_key(level, ix + dx, iy + dy, iz + dz), b, f)) { cs = b; cf = f; }
+      }
+      uint32_t incl = cf;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+      }
+      const uint32_t ps = incl - cf;                               // first flat index of this lane's run
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
       if (total < k_eff) continue;
-      // pass 2: exact top-k over the block
-      tk.reset();
+      // 2. + 3. candidates through the buffer, k best kept at its front
       const float4* sp = g.sorted + (size_t)level * n_max;
-      for (t = 0; t < 27; ++t)
-        for (uint32_t u = cs[t]; u < ce[t]; ++u) {
-          const float4 p = sp[u];
-          tk.push(d2_f32(q.x, q.y, q.z, p.x, p.y, p.z), k_eff);
+      uint32_t m = 0;
+      for (uint32_t c0 = 0; c0 < total;) {
+        const uint32_t take = min((uint32_t)KNN_CAP - m, total - c0);
+        for (uint32_t base = 0; base < take; base += 32) {
+          const uint32_t ci = base + lane;
+          const uint32_t flat = c0 + min(ci, take - 1u);
+          uint32_t run = 0;                                        // largest t with ps[t] <= flat
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t mid = run + step;
+            const uint32_t v = __shfl_sync(0xffffffffu, ps, mid & 31u);
+            if (mid < 27u && v <= flat) run = mid;
+          }
+          const uint32_t rs = __shfl_sync(0xffffffffu, cs, run), rp = __shfl_sync(0xffffffffu, ps, run);
+          if (ci < take) {
+            const float4 p = sp[rs + (flat - rp)];
+            buf[m + ci] = __float_as_uint(d2_f32(q.x, q.y, q.z, p.x, p.y, p.z));
+          }
         }
-      // every point closer than ~c lies inside the block; 0.999 absorbs the rounding of floor(x/c)
-      const float safe = __fmul_rn(c, 0.999f);
-      if (tk.cnt >= k_eff && tk.best[k_eff - 1] <= __fmul_rn(safe, safe)) done = true;
+        __syncwarp();
+        const uint32_t nbuf = m + take;
+        c0 += take;
+        if (nbuf > k_eff) {
+          uint32_t V = 0;                                          // the k-th smallest bit pattern
+          for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = V | (1u << bit);
+            uint32_t below = 0;
+            for (uint32_t i = lane; i < nbuf; i += 32) below += buf[i] < trial ? 1u : 0u;
+            if (__reduce_add_sync(0xffffffffu, below) < k_eff) V = trial;
+          }
+          uint32_t below = 0;
+          for (uint32_t i = lane; i < nbuf; i += 32) below += buf[i] < V ? 1u : 0u;
+          const uint32_t need_eq = k_eff - __reduce_add_sync(0xffffffffu, below);
+          uint32_t kept = 0, eq_seen = 0;
+          for (uint32_t base = 0; base < nbuf; base += 32) {       // in place: writes never pass the batch being read
+            const uint32_t i = base + lane;
+            const uint32_t x = i < nbuf ? buf[i] : 0xffffffffu;
+            const bool is_eq = i < nbuf && x == V;
+            const uint32_t beq = __ballot_sync(0xffffffffu, is_eq);
+            const bool keep = (i < nbuf && x < V) || (is_eq && eq_seen + __popc(beq & lt_mask) < need_eq);
+            const uint32_t bk = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) buf[kept + __popc(bk & lt_mask)] = x;
+            kept += __popc(bk);
+            eq_seen += __popc(beq);
+            __syncwarp();
+          }
+          m = k_eff;
+        } else {
+          m = nbuf;
+        }
+      }
+      // 4. covered by the block?
+      uint32_t mx = 0;
+      for (uint32_t i = lane; i < k_eff; i += 32) mx = max(mx, buf[i]);
+      const float kth = __uint_as_float(__reduce_max_sync(0xffffffffu, mx));
+      const float safe = __fmul_rn(c, 0.999f);   // every point closer than ~c lies inside the block
+      if (kth <= __fmul_rn(safe, safe)) done = true;
     }
-    if (done) avg[orig] = tk.average(k_eff);
-    else stragglers[atomicAdd(&ctrl->counters[CTR_STRAGGLERS], 1u)] = orig;
+    if (done) {
+      for (uint32_t e = lane; e < k_eff; e += 32) {                 // rank sort (k <= 64)
+        const uint32_t x = buf[e];
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < k_eff; ++i) {
+          const uint32_t y = buf[i];
+          rank += (y < x || (y == x && i < e)) ? 1u : 0u;
+        }
+        sorted_k[rank] = x;
+      }
+      __syncwarp();
+      const float r0 = lane < k_eff ? sqrtf(__uint_as_float(sorted_k[lane])) : 0.0f;
+      const float r1 = lane + 32 < k_eff ? sqrtf(__uint_as_float(sorted_k[lane + 32])) : 0.0f;
+      float sum = 0.0f;
+      for (uint32_t i = 0; i < k_eff; ++i) {                         // sequential float32 sum, ascending
+        const float v = __shfl_sync(0xffffffffu, i < 32 ? r0 : r1, i & 31u);
+        sum = i == 0 ? v : __fadd_rn(sum, v);
+      }
+      if (lane == 0) avg[orig] = __fdiv_rn(sum, (float)k_eff);
+      __syncwarp();
+    } else if (lane == 0) {
+      stragglers[atomicAdd(&ctrl->counters[CTR_STRAGGLERS], 1u)] = orig;
+    }
   }
 }
 
@@ -684,10 +777,10 @@ int apc_statistical_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, con
   double* stats = out_stats_dev ? out_stats_dev : sc->stats;
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell_hint, !(cell_hint > 0.0f), s);
   if (rc) return rc;
-  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  const uint32_t bq = min(apc_div_up(n_max, KNN_WARPS), (uint32_t)APC_SM_COUNT * 16);   // one warp per query, grid-stride
   {
     APC_PROF(ctx, "k_knn_query", s);
-    k_knn_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
+    k_knn_query<<<bq, KNN_WARPS * 32, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
   }
   {
     APC_PROF(ctx, "k_knn_stragglers", s);
