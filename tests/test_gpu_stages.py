@@ -284,7 +284,7 @@ def test_statistical_outliers_parity(env):
     far = torch.tensor([[300.0, 300.0, 50.0, 0.0], [-250.0, 40.0, 90.0, 0.0], [1000.0, -900.0, 5.0, 0.0]], device="cuda")
     v = torch.cat([v, far]).contiguous()
     host = v.cpu().numpy()
-    for k, ratio in ((20, 2.0), (8, 1.0)):
+    for k, ratio in ((20, 2.0), (8, 1.0), (32, 2.0), (33, 1.5), (64, 2.0)):     # k <= 32: register lists; above: shared buffer
         for rep in range(2):
             mask, avg, stats = ctx.statistical_outliers(v, k, ratio)
             ctx.check()
