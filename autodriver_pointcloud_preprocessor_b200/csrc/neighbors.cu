@@ -589,6 +589,7 @@ struct NeighborScratch {
   GridHost grid[2];
   uint32_t* stragglers = nullptr;
   double* stats = nullptr;
+  double* cov = nullptr;            // [max_points][9] covariances between k_normals_cov and k_normals_eigen
 };
 // one scratch set per context, keyed by pointer (contexts are few; freed at process exit)
 #include <map>
@@ -617,6 +618,7 @@ void apc_neighbors_release(apc_ctx* ctx) {
   }
   if (s->stragglers) cudaFree(s->stragglers);
   if (s->stats) cudaFree(s->stats);
+  if (s->cov) cudaFree(s->cov);
   delete s;
   g_scratch.erase(it);
 }
@@ -1058,6 +1060,116 @@ k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint
   }
 }
 
+// max_nn <= 32 (the reference's default is 30): one WARP per query, as in k_knn_query.  Lanes 0..26
+// resolve the 27 cells; the lanes stride over the flat candidate list; the max_nn nearest in-radius
+// neighbours by (d2, original index) live in registers, lane i holding the i-th smallest key and the
+// neighbour's position; every lane then contributes its neighbour's moments about the query point
+// and a shuffle tree adds them up in float64.  The eigenvector is computed by k_normals_eigen, one
+// THREAD per point (a serial float64 solve would idle 31 lanes of the warp here).
+__global__ void __launch_bounds__(128)
+k_normals_cov(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t max_nn, uint32_t* __restrict__ counts,
+              double* __restrict__ cov9) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  const float c = grid_cell_size(g, 0);
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5) {
+    const float4 q = g.sorted[j];
+    const uint32_t orig = __float_as_uint(q.w);
+    int32_t ix, iy, iz;
+    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+    uint32_t cs = 0, cf = 0;
+    if (lane < 27) {
+      const int dx = (int)(lane % 3u) - 1, dy = (int)((lane / 3u) % 3u) - 1, dz = (int)(lane / 9u) - 1;
+      uint32_t b, f;
+      if (grid_lookup(g, grid_key(0, ix + dx, iy + dy, iz + dz), b, f)) { cs = b; cf = f; }
+    }
+    uint32_t incl = cf;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t ps = incl - cf;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);   // >= 1: the query's own cell holds the query
+    unsigned long long kv = ~0ull, kth = ~0ull;                   // lane i: i-th smallest key so far / the max_nn-th
+    uint32_t pv = 0, in_radius = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t ci = base + lane;
+      const uint32_t flat = min(ci, total - 1u);
+      uint32_t run = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t mid = run + step;
+        const uint32_t v = __shfl_sync(0xffffffffu, ps, mid & 31u);
+        if (mid < 27u && v <= flat) run = mid;
+      }
+      const uint32_t rs = __shfl_sync(0xffffffffu, cs, run), rp = __shfl_sync(0xffffffffu, ps, run);
+      const uint32_t pos = rs + (flat - rp);
+      unsigned long long key = ~0ull;
+      if (ci < total) {
+        const float4 p = g.sorted[pos];
+        const float d2 = d2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (d2 <= r2) key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+      }
+      in_radius += __popc(__ballot_sync(0xffffffffu, key != ~0ull));
+      uint32_t cand = __ballot_sync(0xffffffffu, key < kth);
+      while (cand) {
+        const uint32_t b = __ffs(cand) - 1u;
+        cand &= cand - 1u;
+        const unsigned long long x = __shfl_sync(0xffffffffu, key, b);
+        const uint32_t xp = __shfl_sync(0xffffffffu, pos, b);
+        if (x < kth) {
+          const uint32_t at = __popc(__ballot_sync(0xffffffffu, kv <= x));
+          const unsigned long long up_k = __shfl_up_sync(0xffffffffu, kv, 1);
+          const uint32_t up_p = __shfl_up_sync(0xffffffffu, pv, 1);
+          if (lane > at) { kv = up_k; pv = up_p; }
+          else if (lane == at) { kv = x; pv = xp; }
+          kth = __shfl_sync(0xffffffffu, kv, max_nn - 1u);
+        }
+      }
+    }
+    const uint32_t n_sel = min(in_radius, max_nn);
+    double C[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};   // fewer than 3 neighbours: identity
+    if (n_sel >= 3) {
+      double v[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (lane < n_sel) {
+        const float4 p = g.sorted[pv];
+        const double x = (double)p.x - (double)q.x, y = (double)p.y - (double)q.y, z = (double)p.z - (double)q.z;
+        v[0] = x; v[1] = y; v[2] = z;
+        v[3] = x * x; v[4] = x * y; v[5] = x * z; v[6] = y * y; v[7] = y * z; v[8] = z * z;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      const double inv = 1.0 / (double)n_sel;
+      const double s0 = v[0] * inv, s1 = v[1] * inv, s2 = v[2] * inv;
+      C[0] = v[3] * inv - s0 * s0;
+      C[1] = C[3] = v[4] * inv - s0 * s1;
+      C[2] = C[6] = v[5] * inv - s0 * s2;
+      C[4] = v[6] * inv - s1 * s1;
+      C[5] = C[7] = v[7] * inv - s1 * s2;
+      C[8] = v[8] * inv - s2 * s2;
+    }
+    if (lane < 9) cov9[9 * (size_t)orig + lane] = C[lane];
+    if (lane == 0 && counts) counts[orig] = n_sel;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_normals_eigen(uint32_t n_max, const uint32_t* n_dev, const double* __restrict__ cov9, float* __restrict__ normals) {
+  const uint32_t n = apc_count(n_dev, n_max);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double C[9], nrm[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) C[k] = cov9[9 * (size_t)i + k];
+    normal_from_covariance(C, nrm);
+    normals[3 * (size_t)i + 0] = (float)nrm[0];
+    normals[3 * (size_t)i + 1] = (float)nrm[1];
+    normals[3 * (size_t)i + 2] = (float)nrm[2];
+  }
+}
+
 int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int max_nn, double radius,
                         float* out_normals, uint32_t* out_counts, double* out_cov, cudaStream_t s) {
   if (n_max == 0) return APC_OK;
@@ -1071,8 +1183,23 @@ int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const u
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s);
   if (rc) return rc;
-  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
-  {
+  if (max_nn <= 32) {
+    // warp per query -> covariances (caller's buffer or context scratch), then thread per point -> eigenvector
+    NeighborScratch* sc = scratch_of(ctx);
+    double* cov = out_cov;
+    if (!cov) {
+      if (!sc->cov) APC_CUDA(ctx, cudaMalloc((void**)&sc->cov, (size_t)ctx->max_points * 9 * sizeof(double)));
+      cov = sc->cov;
+    }
+    const uint32_t bq = min(apc_div_up(n_max, 4), (uint32_t)APC_SM_COUNT * 16);
+    {
+      APC_PROF(ctx, "k_normals_cov", s);
+      k_normals_cov<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_counts, cov);
+    }
+    APC_PROF(ctx, "k_normals_eigen", s);
+    k_normals_eigen<<<min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8), 256, 0, s>>>(n_max, n_dev, cov, out_normals);
+  } else {
+    const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
     APC_PROF(ctx, "k_normals_query", s);
     k_normals_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_normals, out_counts, out_cov);
   }
