@@ -64,10 +64,7 @@ struct apc_ctx {
   uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
   uint32_t* p2slot = nullptr;       // [max_points]
   unsigned long long* dedup_slots = nullptr;  // [hash_cap] {key fingerprint:32 | lowest point index:32}
-  // neighbour grid
-  uint32_t* cell_start = nullptr;   // [hash_cap]
-  uint32_t* cell_fill = nullptr;    // [hash_cap]
-  float4* sorted_pts = nullptr;     // [max_points] xyz + original index bits
+  float4* sorted_pts = nullptr;     // [max_points] NaN-skipped cloud of the sorted duplicate-removal modes
   float* knn_avg = nullptr;         // [max_points]
   double* red_a = nullptr;          // reduction ping-pong
   double* red_b = nullptr;

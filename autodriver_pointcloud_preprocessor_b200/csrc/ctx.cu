@@ -42,6 +42,9 @@ __global__ void k_begin(ApcCtrl* ctrl) {
 }
 
 int apc_begin(apc_ctx* ctx, cudaStream_t s) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device)
+    return apc_set_error(ctx, APC_ERR_BAD_ARG, "the context lives on another device than the calling thread's current one");
   k_begin<<<1, 32, 0, s>>>(ctx->ctrl);
   APC_LAUNCH_CHECK(ctx, "k_begin");
   return APC_OK;
@@ -73,7 +76,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   apc_sort_release(ctx);
   for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
   void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_acc, ctx->vox_rank, ctx->p2slot,
-                  ctx->dedup_slots, ctx->cell_start, ctx->cell_fill, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
+                  ctx->dedup_slots, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_scores_copy, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
                   ctx->mask_a, ctx->idx_a, ctx->idx_b, ctx->dev_counts};
   for (void* p : ptrs)
@@ -116,8 +119,6 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   A(dalloc(&ctx->vox_rank, C));
   A(dalloc(&ctx->p2slot, M));
   A(dalloc(&ctx->dedup_slots, C));
-  A(dalloc(&ctx->cell_start, C));
-  A(dalloc(&ctx->cell_fill, C));
   A(dalloc(&ctx->sorted_pts, M));
   A(dalloc(&ctx->knn_avg, M));
   A(dalloc(&ctx->red_a, red));

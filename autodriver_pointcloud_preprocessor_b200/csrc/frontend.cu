@@ -403,12 +403,14 @@ static int build_params(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
 }
 
 static int set_smem(apc_ctx* ctx, uint32_t smem) {
-  static uint32_t configured = 0;  // both kernels share the limit; opt in once
-  // static shared memory counts against the 48 KB default too, so opt in well below it
-  if (smem > 32 * 1024 && smem > configured) {
+  // the attribute is per device: opt in once on every device a context lives on (both kernels share
+  // the limit); static shared memory counts against the 48 KB default too, so opt in well below it
+  static bool configured[64] = {};
+  const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+  if (smem > 32 * 1024 && !configured[dev]) {
     APC_CUDA(ctx, cudaFuncSetAttribute(k_frontend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
     APC_CUDA(ctx, cudaFuncSetAttribute(k_dedup_insert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
-    configured = 192 * 1024;
+    configured[dev] = true;
   }
   return APC_OK;
 }

@@ -22,8 +22,9 @@
  *     (when non-NULL the kernels read the true size from it) and writes its output size to
  *     a device counter.  Output buffers must hold `n_max` elements.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
- *     asynchronous; a context is bound to one device and must be used from one thread /
- *     stream at a time (the reference runs one callback at a time, pp.py:1056).
+ *     asynchronous; a context is bound to one device (which must be the calling thread's
+ *     current device: APC_ERR_BAD_ARG otherwise) and must be used from one thread / stream
+ *     at a time (the reference runs one callback at a time, pp.py:1056).
  *   - return value: APC_OK or a negative apc_status; apc_last_error(ctx) gives the text.
  *     Data-dependent failures (key range, table capacity) are raised on the device and
  *     reported by apc_check(ctx) after the stream has been synchronised.
