@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define APC_VERSION 100 /* 0.1.0 */
+#define APC_VERSION 110 /* 0.1.1: + apc_unique_rows, apc_estimate_normals, apc_pipeline_run_maps, sorted dedup modes */
 
 typedef enum apc_status {
   APC_OK = 0,
