@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in apc.h but not exported"
     assert sorted(_capi.SYMBOLS) == names          # the ctypes binding covers the whole header
-    assert lib.apc_version() == 100
+    assert lib.apc_version() == 110                 # APC_VERSION in apc.h
 
 
 def test_struct_layouts_match_header():
