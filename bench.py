@@ -335,6 +335,8 @@ def main():
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_begin, time.perf_counter())
+    if world > 1 and pad_rows:                    # the exchanged slabs hold every frame's output in full
+        assert int(counts_arena[:, _capi.CNT_OUTPUT].max().item()) <= pad_rows, "gather slab too small"
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
