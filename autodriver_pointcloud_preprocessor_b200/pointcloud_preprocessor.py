@@ -20,8 +20,9 @@ sorted unique rows, torch -> ``points[inverse]`` exactly as ``utils.py:538-542``
 (N rows), anything else -> Open3D semantics; all three run on the device.
 Normal estimation (``estimate_normals``, default True like the reference) runs on the device
 (``apc_estimate_normals``) and adds ``normal_x/y/z`` to the published cloud (pp.py:560-567).
-Deliberate deviations, all visible: visualisation / PCD saving need Open3D and are skipped with
-a warning.
+``save_pointcloud`` writes uncompressed PCD files of the published layout (``pointcloud_loader``).
+Deliberate deviations, all visible: visualisation and the other file formats need Open3D and are
+skipped with a warning.
 """
 from __future__ import annotations
 
@@ -611,6 +612,7 @@ class PointcloudPreprocessorNode(Node):
             self.processing_times['pointcloud_msg_parsing'] = get_time_difference(start_time, get_current_time(monotonic=True))
 
             start_time = get_current_time(monotonic=True)
+            self._last_output_msg = pc_msg
             self.pointcloud_pub.publish(pc_msg)
             self.processing_times['pointcloud_pub'] = get_time_difference(start_time, get_current_time(monotonic=True))
 
@@ -819,9 +821,21 @@ class PointcloudPreprocessorNode(Node):
         pass
 
     def pointcloud_saver(self, pcd_number):
-        """pp.py:1010-1022 (Open3D file IO; outside the GPU hot path)."""
+        """pp.py:1010-1022.  The reference hands the cloud to Open3D's writers; here the published
+        record layout is written as a PCD v0.7 file (binary, or ascii with ``pointcloud_save_ascii``).
+        Other extensions and ``compressed`` need Open3D's writers and are skipped with a warning."""
         if self.save_pointcloud:
-            self._warn_once("save_pointcloud=True needs Open3D's point-cloud writers; saving is skipped")
+            pointcloud_extension = self.pointcloud_save_extension.strip('.')
+            msg = getattr(self, '_last_output_msg', None)
+            if pointcloud_extension.lower() != 'pcd' or self.pointcloud_save_compressed or msg is None:
+                self._warn_once(f"save_pointcloud: only uncompressed .pcd is written without Open3D "
+                                f"(extension '{pointcloud_extension}', compressed={self.pointcloud_save_compressed}); skipped")
+                return
+            from .pointcloud_loader import write_pcd
+            os.makedirs(self.pointcloud_save_directory, exist_ok=True)
+            pcd_file_name = os.path.join(self.pointcloud_save_directory,
+                                         f"{self.pointcloud_save_prepend_str}{pcd_number}.{pointcloud_extension}")
+            write_pcd(pcd_file_name, msg, binary=not self.pointcloud_save_ascii)
 
     def pointcloud_visualizer(self, pcd_number):
         """pp.py:1024-1050 (Open3D GUI; outside the GPU hot path)."""

@@ -253,3 +253,20 @@ def test_fused_and_staged_paths_publish_the_same_cloud():
     # single-point voxels carry the input's attribute values exactly: most of the cloud at 0.1 m
     exact = (a["ring"] == b["ring"]).mean()
     assert exact > 0.95
+
+
+def test_node_saves_published_cloud_as_pcd(tmp_path):
+    """save_pointcloud (pp.py:1010-1018): the published records land in <dir>/<prefix><frame>.pcd."""
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_loader as pl
+    _, msg = scan_msg("xyzirt22", seed=51, n_beams=16, n_az=512)
+    node = make_node({"use_gpu": True, "voxel_size": 0.2, "estimate_normals": False, "save_pointcloud": True,
+                      "pointcloud_save_directory": str(tmp_path), "pointcloud_save_prepend_str": "scan_"})
+    node.callback(msg)
+    node.callback(msg)
+    out = node.pointcloud_pub.messages[-1]
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["scan_00000000.pcd", "scan_00000001.pcd"]
+    back = pl.read_pcd(str(tmp_path / files[-1]))
+    assert back.width == out.width and back.point_step == out.point_step
+    assert [(f.name, f.offset, f.datatype) for f in back.fields] == [(f.name, f.offset, f.datatype) for f in out.fields]
+    assert bytes(back.data) == bytes(out.data)

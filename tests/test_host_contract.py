@@ -170,3 +170,26 @@ def test_gather_outputs_gloo_world2():
             for j, f in enumerate(range(g * 3, g * 3 + 3)):
                 assert counts[g, j] == f % 4 + 1
                 assert (recv[g, j, :counts[g, j]] == f).all() and (recv[g, j, counts[g, j]:] == 0).all()
+
+
+def test_pcd_loader_round_trip(tmp_path):
+    """File replay shell (pointcloud_loader.py:1-5 states the intent only): binary and ascii PCD files
+    become the PointCloud2 byte buffers a driver would publish, in name order, optionally looping."""
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_loader as pl
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    from oracle import pc2
+    scan = synth.lidar_scan(seed=3, n_beams=8, n_az=64)
+    msg = synth.pack_cloud(scan, "xyzirt22")
+    for k, binary in enumerate((True, False)):
+        pl.write_pcd(str(tmp_path / f"scan_{k}.pcd"), msg, binary=binary)
+    replay = pl.DirectoryReplay(str(tmp_path))
+    assert len(replay) == 2
+    want = np.frombuffer(bytes(msg.data), dtype=pc2.dtype_from_fields(msg.fields, msg.point_step))
+    for got_msg in replay:
+        assert [(f.name, f.offset, f.datatype) for f in got_msg.fields] == [(f.name, f.offset, f.datatype) for f in msg.fields]
+        assert got_msg.width == msg.width and got_msg.point_step == msg.point_step and not got_msg.is_dense
+        got = np.frombuffer(bytes(got_msg.data), dtype=pc2.dtype_from_fields(got_msg.fields, got_msg.point_step))
+        for name in want.dtype.names:
+            assert np.array_equal(got[name], want[name], equal_nan=True), name      # repr() round-trips floats exactly
+    looping = iter(pl.DirectoryReplay(str(tmp_path), loop=True))
+    assert [next(looping).width for _ in range(5)] == [msg.width] * 5
