@@ -23,6 +23,8 @@ try:  # pragma: no cover - not available in the build image
     import tf2_ros
     from tf2_ros import Buffer, TransformListener, LookupException, ConnectivityException, ExtrapolationException
     from sensor_msgs_py import point_cloud2
+    from rclpy.duration import Duration
+    from rclpy.time import Time
     HAVE_ROS = True
 except ImportError:
     HAVE_ROS = False
@@ -95,6 +97,24 @@ except ImportError:
         def __init__(self, reliability=QoSReliabilityPolicy.RELIABLE, history=QoSHistoryPolicy.KEEP_LAST, depth=1):
             self.reliability, self.history, self.depth = reliability, history, depth
 
+    class Duration:
+        """rclpy.duration.Duration stand-in (pp.py:718 wraps transform_timeout in one)."""
+
+        def __init__(self, *, seconds=0.0, nanoseconds=0):
+            self.nanoseconds = int(round(float(seconds) * 1e9)) + int(nanoseconds)
+
+    class Time:
+        """rclpy.time.Time stand-in (pp.py:477 converts the header stamp with Time.from_msg)."""
+
+        def __init__(self, *, seconds=0, nanoseconds=0):
+            self.nanoseconds = int(seconds) * 1_000_000_000 + int(nanoseconds)
+
+        @classmethod
+        def from_msg(cls, msg):
+            if msg is None:
+                return cls()
+            return cls(seconds=getattr(msg, "sec", 0), nanoseconds=getattr(msg, "nanosec", 0))
+
     class LookupException(Exception):
         pass
 
@@ -123,6 +143,11 @@ except ImportError:
             self._tf[(target_frame, source_frame)] = TransformStamped(translation, rotation_xyzw)
 
         def lookup_transform(self, target_frame, source_frame, time=None, timeout=None):
+            # tf2_ros.Buffer computes `start_time + timeout`: anything but a Duration / Time pair raises
+            if timeout is not None and not isinstance(timeout, Duration):
+                raise TypeError("lookup_transform: timeout must be a Duration (tf2_ros.Buffer signature)")
+            if time is not None and not isinstance(time, Time):
+                raise TypeError("lookup_transform: time must be a Time (tf2_ros.Buffer signature)")
             try:
                 return self._tf[(target_frame, source_frame)]
             except KeyError:

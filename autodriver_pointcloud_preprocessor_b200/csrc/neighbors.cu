@@ -182,11 +182,20 @@ __device__ __forceinline__ float d2_f32(float ax, float ay, float az, float bx, 
 __constant__ int8_t c_cell_order[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25,
                                          0, 2, 6, 8, 18, 20, 24, 26};
 
+// Number of valid records at the front of the level-0 cell-sorted array: the scatter cursor, i.e. the
+// points that were actually inserted.  Points that failed grid_coord (non-finite or beyond the key
+// range; APC_ERR_KEY_RANGE is raised for them) are never scattered, so the tail of `sorted` beyond
+// the cursor holds stale records of an earlier frame whose `orig` may exceed this frame's size: the
+// query kernels must not walk it.
+__device__ __forceinline__ uint32_t grid_sorted_count(const GridDev& g, const ApcCtrl* ctrl, uint32_t n) {
+  return min(n, ctrl->counters[g.cursor_base]);
+}
+
 // ---- radius query -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
-               uint8_t* __restrict__ mask, uint32_t* __restrict__ counts) {
-  const uint32_t n = apc_count(n_dev, n_max);
+               uint8_t* __restrict__ mask, uint32_t* __restrict__ counts, const ApcCtrl* __restrict__ ctrl) {
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
   const float c = grid_cell_size(g, 0);
   APC_STAMP(0, 0);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -273,12 +282,13 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
             uint32_t* __restrict__ stragglers, ApcCtrl* ctrl) {
   __shared__ uint32_t s_buf[KNN_WARPS][KNN_CAP];
   const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t n_sorted = grid_sorted_count(g, ctrl, n);
   const uint32_t k_eff = min(k, n);
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t* buf = s_buf[w];
   uint32_t* sorted_k = buf + KNN_CAP / 2;          // free once the k best sit at the front (k <= 64)
-  for (uint32_t j = blockIdx.x * KNN_WARPS + w; j < n; j += gridDim.x * KNN_WARPS) {
+  for (uint32_t j = blockIdx.x * KNN_WARPS + w; j < n_sorted; j += gridDim.x * KNN_WARPS) {
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
     bool done = false;
@@ -704,7 +714,7 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   {
     APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts, ctx->ctrl);
   }
   const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
   APC_PROF(ctx, "k_grid_clean", s);
@@ -788,7 +798,7 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   {
     APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)nb_points, 0, mask_scratch, nullptr);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)nb_points, 0, mask_scratch, nullptr, ctx->ctrl);
   }
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
@@ -807,6 +817,9 @@ extern "C" int apc_radius_outliers(apc_ctx* ctx, const float* xyzi, uint32_t n_m
   cudaStream_t s = (cudaStream_t)stream;
   int rc = apc_begin(ctx, s);
   if (rc) return rc;
+  // points outside the grid's key range (APC_ERR_KEY_RANGE at apc_check) are never queried: defined result
+  if (out_mask && n_max) APC_CUDA(ctx, cudaMemsetAsync(out_mask, 0, n_max, s));
+  if (out_neighbor_counts && n_max) APC_CUDA(ctx, cudaMemsetAsync(out_neighbor_counts, 0, (size_t)n_max * sizeof(uint32_t), s));
   return apc_radius_nobegin(ctx, xyzi, n_max, n_dev, nb_points, radius, out_mask, out_neighbor_counts, s);
 }
 
@@ -1008,8 +1021,8 @@ __device__ void normal_from_covariance(const double* C, double* nrm) {
 
 __global__ void __launch_bounds__(128)
 k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t max_nn, float* __restrict__ normals,
-                uint32_t* __restrict__ counts, double* __restrict__ covariances) {
-  const uint32_t n = apc_count(n_dev, n_max);
+                uint32_t* __restrict__ counts, double* __restrict__ covariances, const ApcCtrl* __restrict__ ctrl) {
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
   const float c = grid_cell_size(g, 0);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const float4 q = g.sorted[j];
@@ -1068,8 +1081,8 @@ k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint
 // THREAD per point (a serial float64 solve would idle 31 lanes of the warp here).
 __global__ void __launch_bounds__(128)
 k_normals_cov(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t max_nn, uint32_t* __restrict__ counts,
-              double* __restrict__ cov9) {
-  const uint32_t n = apc_count(n_dev, n_max);
+              double* __restrict__ cov9, const ApcCtrl* __restrict__ ctrl) {
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
   const float c = grid_cell_size(g, 0);
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += (gridDim.x * blockDim.x) >> 5) {
@@ -1194,14 +1207,14 @@ int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const u
     const uint32_t bq = min(apc_div_up(n_max, 4), (uint32_t)APC_SM_COUNT * 16);
     {
       APC_PROF(ctx, "k_normals_cov", s);
-      k_normals_cov<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_counts, cov);
+      k_normals_cov<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_counts, cov, ctx->ctrl);
     }
     APC_PROF(ctx, "k_normals_eigen", s);
     k_normals_eigen<<<min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8), 256, 0, s>>>(n_max, n_dev, cov, out_normals);
   } else {
     const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
     APC_PROF(ctx, "k_normals_query", s);
-    k_normals_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_normals, out_counts, out_cov);
+    k_normals_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)max_nn, out_normals, out_counts, out_cov, ctx->ctrl);
   }
   const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
   APC_PROF(ctx, "k_grid_clean", s);
@@ -1217,5 +1230,8 @@ extern "C" int apc_estimate_normals(apc_ctx* ctx, const float* xyzi, uint32_t n_
   cudaStream_t s = (cudaStream_t)stream;
   int rc = apc_begin(ctx, s);
   if (rc) return rc;
+  // points outside the grid's key range (APC_ERR_KEY_RANGE at apc_check) are never queried: defined result
+  if (out_normals && n_max) APC_CUDA(ctx, cudaMemsetAsync(out_normals, 0, (size_t)n_max * 3 * sizeof(float), s));
+  if (out_neighbor_counts && n_max) APC_CUDA(ctx, cudaMemsetAsync(out_neighbor_counts, 0, (size_t)n_max * sizeof(uint32_t), s));
   return apc_normals_nobegin(ctx, xyzi, n_max, n_dev, max_nn, radius, out_normals, out_neighbor_counts, out_covariances, s);
 }

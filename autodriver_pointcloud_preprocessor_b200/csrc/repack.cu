@@ -7,7 +7,7 @@
 // zeros) and ships each tile to HBM with a single TMA bulk store, so the host needs one D2H.
 #include "apc_load.cuh"
 
-#define RP_MAX_FIELDS 16
+#define RP_MAX_FIELDS 64   // the reference has no limit; 64 fields of a <= 192-byte record (1.5 KB of kernel parameters)
 
 struct RepackField {
   int32_t offset, datatype, source, attr_datatype;
@@ -116,7 +116,7 @@ extern "C" int apc_repack(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const
   if (!ctx) return APC_ERR_BAD_ARG;
   if (n_max == 0) return APC_OK;
   APC_REQUIRE(ctx, xyzi && out_bytes && fields, "NULL pointer");
-  APC_REQUIRE(ctx, n_fields >= 1 && n_fields <= RP_MAX_FIELDS, "n_fields must be in 1..16");
+  APC_REQUIRE(ctx, n_fields >= 1 && n_fields <= RP_MAX_FIELDS, "n_fields must be in 1..64");
   APC_REQUIRE(ctx, point_step >= 1 && point_step <= 192, "point_step must be 1..192");
   RepackParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -132,10 +132,11 @@ extern "C" int apc_repack(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const
   prm.n_fields = n_fields;
   prm.step = point_step;
   const uint32_t smem = APC_TILE_POINTS * point_step + 16;
-  static bool configured = false;
-  if (smem > 32 * 1024 && !configured) {
+  static bool configured[64] = {};   // the attribute is per device (as in frontend.cu set_smem)
+  const int dev = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+  if (smem > 32 * 1024 && !configured[dev]) {
     APC_CUDA(ctx, cudaFuncSetAttribute(k_repack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured[dev] = true;
   }
   APC_PROF(ctx, "k_repack", (cudaStream_t)stream);
   k_repack<<<apc_div_up(n_max, APC_TILE_POINTS), APC_TILE_THREADS, smem, (cudaStream_t)stream>>>(

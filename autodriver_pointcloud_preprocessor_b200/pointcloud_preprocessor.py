@@ -47,10 +47,10 @@ import torch
 from . import _capi, engine, geometry
 from . import geometry as o3d
 from . import geometry as o3c
-from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, ExtrapolationException, Header,  # noqa: F401
+from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, Duration, ExtrapolationException, Header,  # noqa: F401
                           LookupException, Node, Parameter, ParameterDescriptor, ParameterType, PointCloud2,
                           PointField, QoSHistoryPolicy, QoSProfile, QoSReliabilityPolicy, SetParametersResult,
-                          TransformListener, point_cloud2, rclpy, tf2_ros)
+                          Time, TransformListener, point_cloud2, rclpy, tf2_ros)
 from .utils import (raw_column, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
                     convert_pointcloud_to_numpy, crop_pointcloud, dict_to_open3d_tensor_pointcloud,
                     extract_rgb_from_pointcloud, get_current_time, get_fields_from_dicts, get_pointcloud_metadata,
@@ -381,7 +381,7 @@ class PointcloudPreprocessorNode(Node):
         # transform lookup first (needed by both paths; pp.py:475-478)
         start_time = get_current_time(monotonic=True)
         self.get_camera_to_robot_tf(self.pointcloud_metadata["header"].frame_id,
-                                    getattr(self.pointcloud_metadata["header"], 'stamp', None))
+                                    Time.from_msg(getattr(self.pointcloud_metadata["header"], 'stamp', None)))
         self.processing_times['tf_lookup'] = get_time_difference(start_time, get_current_time(monotonic=True))
         if self._use_fused() and self._raw_msg is not None:
             return self._preprocess_fused()
@@ -628,10 +628,12 @@ class PointcloudPreprocessorNode(Node):
         """pp.py:704-732."""
         if self.camera_to_robot_tf is not None and self.static_camera_to_robot_tf:
             return
+        if timestamp is None:
+            timestamp = Time()
         if self.robot_frame:
             try:
                 transform = self.tf_buffer.lookup_transform(self.robot_frame, source_frame_id, timestamp,
-                                                            self.transform_timeout)
+                                                            Duration(seconds=self.transform_timeout))
             except tf2_ros.LookupException as e:
                 self.get_logger().error(f"TF Lookup Error: {str(e)}")
                 return

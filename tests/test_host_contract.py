@@ -193,3 +193,36 @@ def test_pcd_loader_round_trip(tmp_path):
             assert np.array_equal(got[name], want[name], equal_nan=True), name      # repr() round-trips floats exactly
     looping = iter(pl.DirectoryReplay(str(tmp_path), loop=True))
     assert [next(looping).width for _ in range(5)] == [msg.width] * 5
+
+
+def test_tf_lookup_uses_duration_and_time_like_the_reference():
+    """pp.py:476-477,714-719: the stamp goes through rclpy.time.Time.from_msg and the timeout through
+    rclpy.duration.Duration; tf2_ros.Buffer adds them, so a bare float raises TypeError there.  The
+    stand-in buffer enforces the same signature, and the node must call it accordingly."""
+    from autodriver_pointcloud_preprocessor_b200 import _ros_compat as rc
+    from autodriver_pointcloud_preprocessor_b200 import msgs
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_preprocessor as pp
+    if rc.HAVE_ROS:
+        pytest.skip("real tf2_ros present")
+    buf = rc.Buffer()
+    buf.set_transform("base_link", "lidar", (1.0, 2.0, 3.0), (0.0, 0.0, 0.0, 1.0))
+    with pytest.raises(TypeError):
+        buf.lookup_transform("base_link", "lidar", rc.Time(), 0.1)
+    with pytest.raises(TypeError):
+        buf.lookup_transform("base_link", "lidar", msgs.Header().stamp, rc.Duration(seconds=0.1))
+    assert buf.lookup_transform("base_link", "lidar", rc.Time.from_msg(msgs.Header().stamp),
+                                rc.Duration(seconds=0.1)).transform.translation.x == 1.0
+
+    class Fake:                                       # just enough of the node for get_camera_to_robot_tf
+        camera_to_robot_tf, static_camera_to_robot_tf = None, True
+        robot_frame, transform_timeout, tf_buffer = "base_link", 0.1, buf
+
+        def transform_to_matrix(self, t):
+            return ("matrix", t.transform.translation.y)
+
+    node = Fake()
+    pp.PointcloudPreprocessorNode.get_camera_to_robot_tf(node, "lidar", rc.Time.from_msg(msgs.Header().stamp))
+    assert node.camera_to_robot_tf == ("matrix", 2.0)
+    node.camera_to_robot_tf = None
+    pp.PointcloudPreprocessorNode.get_camera_to_robot_tf(node, "lidar")      # timestamp=None -> Time()
+    assert node.camera_to_robot_tf == ("matrix", 2.0)
