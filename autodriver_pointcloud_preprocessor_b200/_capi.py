@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(PKG, "libapc.so")
 APC_MAX_FIELDS = 16
 APC_MAX_CLOUDS = 8
 APC_MAX_TRANSFORMS = 3
+APC_MAX_MIRRORS = 8
 
 APC_OK, APC_ERR_CUDA, APC_ERR_BAD_ARG, APC_ERR_KEY_RANGE, APC_ERR_CAPACITY, APC_ERR_TOO_FEW = 0, -1, -2, -3, -4, -5
 CROP_NUMPY, CROP_TORCH, CROP_OPEN3D = 0, 1, 2
@@ -50,7 +51,12 @@ class OutField(C.Structure):
 
 class PipelineMaps(C.Structure):
     _fields_ = [("src_idx_dev", C.c_void_p), ("p2v_dev", C.c_void_p), ("voxel_counts_dev", C.c_void_p),
-                ("out_row_dev", C.c_void_p)]
+                ("out_row_dev", C.c_void_p), ("normals_dev", C.c_void_p)]
+
+
+class OutMirror(C.Structure):
+    _fields_ = [("n_xyzi", C.c_uint32), ("xyzi_multicast", C.c_int32), ("xyzi_dev", C.c_void_p * APC_MAX_MIRRORS),
+                ("n_counts", C.c_uint32), ("counts_dev", C.c_void_p * APC_MAX_MIRRORS)]
 
 
 class PipelineCfg(C.Structure):
@@ -60,7 +66,8 @@ class PipelineCfg(C.Structure):
                 ("radius_search_radius", C.c_double),
                 ("ground_enable", C.c_int32), ("ground_distance_threshold", C.c_double),
                 ("ground_ransac_n", C.c_int32), ("ground_num_iterations", C.c_int32),
-                ("ground_probability", C.c_double), ("ground_seed", C.c_uint64)]
+                ("ground_probability", C.c_double), ("ground_seed", C.c_uint64),
+                ("normals_enable", C.c_int32), ("normals_max_nn", C.c_int32), ("normals_radius", C.c_double)]
 
 
 def _load():
@@ -99,6 +106,14 @@ def _load():
                                   C.POINTER(PipelineMaps), vp],
         "apc_graph_capture_pipeline": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
                                        C.POINTER(vp)],
+        "apc_pipeline_run_ex": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
+                                C.POINTER(PipelineMaps), C.POINTER(OutMirror), vp],
+        "apc_graph_capture_pipeline_ex": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
+                                          C.POINTER(PipelineMaps), C.POINTER(OutMirror), C.POINTER(vp)],
+        "apc_pipeline_run_mirrored": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
+                                      C.POINTER(OutMirror), vp],
+        "apc_graph_capture_pipeline_mirrored": [vp, C.POINTER(CloudDesc), u32, C.POINTER(PipelineCfg), vp, vp, vp,
+                                                C.POINTER(OutMirror), C.POINTER(vp)],
         "apc_graph_launch": [vp, vp, vp],
         "apc_graph_destroy": [vp],
         "apc_graph_kernel_count": [vp],
@@ -124,7 +139,9 @@ SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
            "apc_statistical_outliers", "apc_estimate_normals", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run", "apc_pipeline_run_maps",
-           "apc_graph_capture_pipeline", "apc_graph_launch", "apc_graph_destroy",
+           "apc_pipeline_run_mirrored", "apc_pipeline_run_ex", "apc_graph_capture_pipeline_ex",
+           "apc_graph_capture_pipeline", "apc_graph_capture_pipeline_mirrored",
+           "apc_graph_launch", "apc_graph_destroy",
            "apc_graph_kernel_count", "apc_profile_enable", "apc_profile_report", "apc_pack_xyzi",
            "apc_split_xyzi"]
 

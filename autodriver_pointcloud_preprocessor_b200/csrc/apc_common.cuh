@@ -88,6 +88,7 @@ struct apc_ctx {
   uint32_t* sort_hist = nullptr;    // [12][256] digit histograms
   uint64_t* sort_status = nullptr;  // [sort tiles][256] look-back words
   uint32_t* sort_idx = nullptr;     // [max_points] first-index / inverse list of the pipeline's sort modes
+  float* nrm_scratch = nullptr;     // [3 * max_points] normals of the cloud entering the ground stage (pipeline), on first use
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.
@@ -181,6 +182,29 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
+}
+
+// ---- mirrored output rows (multi-GPU exchange fused into the final stage) ---------------------
+// The batched replay configuration ends with "every GPU holds every GPU's output"
+// (BASELINE.json north_star).  Instead of gathering finished slabs with
+// copy engines or NCCL afterwards, the kernel that writes the final cloud also stores every
+// surviving row into the peers' buffers over NVLink (peer-mapped pointers; entry 0 may be an NVLS
+// multicast address, written once and replicated by the switch): only real rows travel, there is
+// no padding, no staging copy and no second read of the slab.
+struct MirrorDev {
+  uint32_t n;          // destinations besides the local output (0 = none)
+  uint32_t multicast;  // != 0: out[0] is a multicast address (multimem.st)
+  float4* out[APC_MAX_MIRRORS];
+};
+__device__ __forceinline__ void mirror_store(const MirrorDev& m, uint32_t row, float4 v) {
+  for (uint32_t k = 0; k < m.n; ++k) {
+    if (k == 0 && m.multicast)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m.out[0] + row), "f"(v.x),
+                   "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    else
+      m.out[k][row] = v;
+  }
 }
 
 // 64-bit mix (splitmix64 finaliser) used as the hash of packed keys

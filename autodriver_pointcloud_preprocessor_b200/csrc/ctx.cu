@@ -78,7 +78,7 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   void* ptrs[] = {ctx->ctrl, ctx->vox_slots, ctx->vox_acc, ctx->vox_rank, ctx->p2slot,
                   ctx->dedup_slots, ctx->sorted_pts, ctx->knn_avg, ctx->red_a,
                   ctx->red_b, ctx->nb_count, ctx->rs_planes, ctx->rs_scores, ctx->rs_scores_copy, ctx->rs_partials, ctx->buf_a, ctx->buf_b,
-                  ctx->mask_a, ctx->idx_a, ctx->idx_b, ctx->dev_counts};
+                  ctx->mask_a, ctx->idx_a, ctx->idx_b, ctx->dev_counts, ctx->nrm_scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto* p : ctx->scan_state)

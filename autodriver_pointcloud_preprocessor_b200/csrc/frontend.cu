@@ -679,7 +679,8 @@ extern "C" int apc_duplicate_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_ma
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev, const uint8_t* __restrict__ mask,
                  int invert, float4* __restrict__ out, uint32_t* __restrict__ out_idx, uint32_t* out_count,
-                 uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles, const uint32_t* __restrict__ idx_in) {
+                 uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles, const uint32_t* __restrict__ idx_in,
+                 const __grid_constant__ MirrorDev mir) {
   __shared__ uint32_t sm_scan[34];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
@@ -705,6 +706,7 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
     if (keep[j]) {
       const uint32_t o = base + rank[j];
       if (out) out[o] = v[j];
+      mirror_store(mir, o, v[j]);
       if (out_idx) {   // index of the survivor in this stage's input, or (idx_in) in an earlier stage's
         const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
         out_idx[o] = idx_in ? idx_in[i] : i;
@@ -716,8 +718,10 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
 
 int apc_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
                        const uint8_t* mask, int invert, float* out_xyzi, uint32_t* out_idx,
-                       uint32_t* out_count_dev, int scan_slot, cudaStream_t s, const uint32_t* idx_in) {
+                       uint32_t* out_count_dev, int scan_slot, cudaStream_t s, const uint32_t* idx_in,
+                       const MirrorDev* mir) {
   APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
+  APC_REQUIRE(ctx, !mir || mir->n == 0 || xyzi, "mirrored output needs the point rows");
   if (n_max == 0) {
     APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
     return APC_OK;
@@ -728,7 +732,8 @@ int apc_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   APC_PROF(ctx, "k_select_by_mask", s);
   k_select_by_mask<<<n_tiles, APC_TILE_THREADS, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, mask, invert,
                                                         reinterpret_cast<float4*>(out_xyzi), out_idx, out_count_dev,
-                                                        ctx->scan_state[scan_slot], ctx->ctrl, n_tiles, idx_in);
+                                                        ctx->scan_state[scan_slot], ctx->ctrl, n_tiles, idx_in,
+                                                        mir ? *mir : MirrorDev{});
   APC_LAUNCH_CHECK(ctx, "k_select_by_mask");
   return APC_OK;
 }
@@ -740,7 +745,7 @@ extern "C" int apc_select_by_mask(apc_ctx* ctx, const float* xyzi, uint32_t n_ma
   cudaStream_t s = (cudaStream_t)stream;
   int rc = apc_begin(ctx, s);
   if (rc) return rc;
-  return apc_select_nobegin(ctx, xyzi, n_max, n_dev, mask, invert, out_xyzi, out_idx, out_count_dev, 0, s, nullptr);
+  return apc_select_nobegin(ctx, xyzi, n_max, n_dev, mask, invert, out_xyzi, out_idx, out_count_dev, 0, s, nullptr, nullptr);
 }
 
 template <typename T>

@@ -27,6 +27,8 @@ APC_TRACE_EXPORT(neighbors)
 #define CTR_STRAGGLERS 12
 #define CTR_CURSOR_RADIUS 13  // scatter cursor of the single-level radius / normals grid
 #define CTR_BBOX 14         // 6 ordered-int floats: min xyz, max xyz
+#define CTR_CURSOR_NORMALS 22  // scatter cursor of the normals stage's grid build (the radius stage of the same
+                               // pipeline run has already advanced CTR_CURSOR_RADIUS)
 
 // whole slot in one read-only 128-bit load (the table is not written while a query kernel runs)
 __device__ __forceinline__ uint4 grid_load(const GridDev& g, uint32_t s) {
@@ -670,7 +672,8 @@ int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s) {
 }
 
 static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_max, const uint32_t* n_dev,
-                      float cell_hint, bool need_bbox, cudaStream_t s, bool inserted = false) {
+                      float cell_hint, bool need_bbox, cudaStream_t s, bool inserted = false, uint32_t cursor_base = 0) {
+  if (g.d.levels == 1) g.d.cursor_base = cursor_base ? cursor_base : CTR_CURSOR_RADIUS;
   const uint32_t bx = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
   if (need_bbox) {
     k_bbox_init<<<1, 32, 0, s>>>(ctx->ctrl);
@@ -729,7 +732,8 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
 __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n_dev, const uint8_t* __restrict__ mask,
                 GridDev g, float4* __restrict__ out, uint32_t* out_count, uint64_t* scan_state, const ApcCtrl* ctrl,
-                uint32_t n_tiles, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ out_idx) {
+                uint32_t n_tiles, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ out_idx,
+                const __grid_constant__ MirrorDev mir) {
   __shared__ uint32_t sm_scan[34];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
@@ -756,6 +760,7 @@ k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n
   for (int j = 0; j < APC_TILE_ITEMS; ++j)
     if (keep[j]) {
       out[base + rank[j]] = v[j];
+      mirror_store(mir, base + rank[j], v[j]);
       if (out_idx) {
         const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
         out_idx[base + rank[j]] = idx_in ? idx_in[i] : i;
@@ -779,7 +784,7 @@ int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
 int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int nb_points,
                               double radius, uint8_t* mask_scratch, float* out_xyzi, uint32_t* out_count_dev,
                               int scan_slot, int points_inserted, cudaStream_t s, const uint32_t* idx_in,
-                              uint32_t* out_idx) {
+                              uint32_t* out_idx, const MirrorDev* mir) {
   APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
   if (n_max == 0) {
     APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
@@ -805,7 +810,7 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   APC_PROF(ctx, "k_radius_select", s);
   k_radius_select<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, mask_scratch, g.d, reinterpret_cast<float4*>(out_xyzi),
                                                        out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles,
-                                                       idx_in, out_idx);
+                                                       idx_in, out_idx, mir ? *mir : MirrorDev{});
   APC_LAUNCH_CHECK(ctx, "radius_select");
   return APC_OK;
 }
@@ -1183,6 +1188,15 @@ k_normals_eigen(uint32_t n_max, const uint32_t* n_dev, const double* __restrict_
   }
 }
 
+// Allocations of the normals stage (grid + covariance scratch): must run outside stream capture.
+int apc_normals_prepare(apc_ctx* ctx, int max_nn) {
+  int rc = apc_neighbors_prepare(ctx, 0);
+  if (rc) return rc;
+  NeighborScratch* sc = scratch_of(ctx);
+  if (max_nn <= 32 && !sc->cov) APC_CUDA(ctx, cudaMalloc((void**)&sc->cov, (size_t)ctx->max_points * 9 * sizeof(double)));
+  return APC_OK;
+}
+
 int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev, int max_nn, double radius,
                         float* out_normals, uint32_t* out_counts, double* out_cov, cudaStream_t s) {
   if (n_max == 0) return APC_OK;
@@ -1194,7 +1208,7 @@ int apc_normals_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const u
   GridHost& g = scratch_of(ctx)->grid[0];
   const float r32 = (float)radius;
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
-  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s, false, CTR_CURSOR_NORMALS);
   if (rc) return rc;
   if (max_nn <= 32) {
     // warp per query -> covariances (caller's buffer or context scratch), then thread per point -> eigenvector

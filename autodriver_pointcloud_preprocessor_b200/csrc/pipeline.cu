@@ -15,31 +15,44 @@ int apc_voxel_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, float, 
                       int, const GridDev*, cudaStream_t);
 int apc_radius_grid_view(apc_ctx*, double, GridDev*);
 int apc_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, const uint8_t*, int, float*, uint32_t*,
-                       uint32_t*, int, cudaStream_t, const uint32_t*);
+                       uint32_t*, int, cudaStream_t, const uint32_t*, const MirrorDev*);
 int apc_radius_select_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, uint8_t*, float*, uint32_t*, int,
-                              int, cudaStream_t, const uint32_t*, uint32_t*);
+                              int, cudaStream_t, const uint32_t*, uint32_t*, const MirrorDev*);
 int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float, uint8_t*, float*,
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
                               const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t,
-                              const uint32_t*, uint32_t*);
+                              const uint32_t*, uint32_t*, const MirrorDev*, const float*, float*);
+int apc_normals_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float*, uint32_t*, double*, cudaStream_t);
 int apc_neighbors_prepare(apc_ctx*, int);
+int apc_normals_prepare(apc_ctx*, int);
 int apc_sort_prepare(apc_ctx*);
 
 // dev_counts layout inside the context
 enum { DC_FILTERED = 1, DC_VOXELS = 2, DC_STAT = 3, DC_RADIUS = 4, DC_OUT = 6, DC_INFO = 8 /* 4 words */ };
 
+struct CountMirrors {
+  uint32_t n;
+  uint32_t* out[APC_MAX_MIRRORS];
+};
 __global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t last, int has_vox, int has_stat,
-                                  int has_rad, int has_ground, const ApcCtrl* ctrl, uint32_t* out) {
-  out[APC_CNT_INPUT] = n_input;
-  out[APC_CNT_FILTERED] = dc[DC_FILTERED];
+                                  int has_rad, int has_ground, const ApcCtrl* ctrl, uint32_t* out,
+                                  const __grid_constant__ CountMirrors mir) {
+  uint32_t c[8];
+  c[APC_CNT_INPUT] = n_input;
+  c[APC_CNT_FILTERED] = dc[DC_FILTERED];
   uint32_t cur = dc[DC_FILTERED];
-  out[APC_CNT_VOXELS] = cur = has_vox ? dc[DC_VOXELS] : cur;
-  out[APC_CNT_AFTER_STAT] = cur = has_stat ? dc[DC_STAT] : cur;
-  out[APC_CNT_AFTER_RADIUS] = cur = has_rad ? dc[DC_RADIUS] : cur;
-  out[APC_CNT_GROUND_INLIERS] = has_ground ? dc[DC_INFO + 1] : 0u;
-  out[APC_CNT_OUTPUT] = dc[last];
-  out[APC_CNT_STATUS] = ctrl->err;
+  c[APC_CNT_VOXELS] = cur = has_vox ? dc[DC_VOXELS] : cur;
+  c[APC_CNT_AFTER_STAT] = cur = has_stat ? dc[DC_STAT] : cur;
+  c[APC_CNT_AFTER_RADIUS] = cur = has_rad ? dc[DC_RADIUS] : cur;
+  c[APC_CNT_GROUND_INLIERS] = has_ground ? dc[DC_INFO + 1] : 0u;
+  c[APC_CNT_OUTPUT] = dc[last];
+  c[APC_CNT_STATUS] = ctrl->err;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = c[k];
+  for (uint32_t m = 0; m < mir.n; ++m)      // the peers' copies of this frame's counters (see apc_out_mirror)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mir.out[m][k] = c[k];
   APC_STAMP(0, 0);
 }
 
@@ -50,19 +63,42 @@ __global__ void k_iota(uint32_t* out, uint32_t n_max, const uint32_t* n_dev) {
 
 static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds, const apc_pipeline_cfg* cfg,
                         float* out_xyzi, uint32_t* out_counts_dev, double* out_plane_dev, cudaStream_t s,
-                        const apc_pipeline_maps* maps = nullptr) {
+                        const apc_pipeline_maps* maps = nullptr, const apc_out_mirror* mirror = nullptr) {
   APC_REQUIRE(ctx, clouds && cfg && out_xyzi && out_counts_dev, "NULL pointer");
+  MirrorDev mir{};
+  CountMirrors cmir{};
+  if (mirror) {
+    APC_REQUIRE(ctx, mirror->n_xyzi <= APC_MAX_MIRRORS && mirror->n_counts <= APC_MAX_MIRRORS, "too many mirrors");
+    APC_REQUIRE(ctx, mirror->n_xyzi == 0 || cfg->stat_enable || cfg->radius_enable || cfg->ground_enable,
+                "mirrored output rows need a selection stage (outlier or ground removal) at the end of the pipeline");
+    mir.n = mirror->n_xyzi;
+    mir.multicast = mirror->xyzi_multicast != 0;
+    for (uint32_t k = 0; k < mir.n; ++k) {
+      APC_REQUIRE(ctx, mirror->xyzi_dev[k], "mirror pointer is NULL");
+      mir.out[k] = reinterpret_cast<float4*>(mirror->xyzi_dev[k]);
+    }
+    cmir.n = mirror->n_counts;
+    for (uint32_t k = 0; k < cmir.n; ++k) {
+      APC_REQUIRE(ctx, mirror->counts_dev[k], "mirror pointer is NULL");
+      cmir.out[k] = mirror->counts_dev[k];
+    }
+  }
   uint32_t n_total = 0;
   for (uint32_t i = 0; i < n_clouds && i < APC_MAX_CLOUDS; ++i) n_total += clouds[i].n_points;
   const bool has_vox = cfg->voxel_size > 0.0f;
   const bool has_stat = cfg->stat_enable != 0, has_rad = cfg->radius_enable != 0, has_ground = cfg->ground_enable != 0;
   const int n_stages = 1 + has_vox + has_stat + has_rad + has_ground;
+  const bool has_normals = cfg->normals_enable != 0;
+  APC_REQUIRE(ctx, !has_normals || (maps && maps->normals_dev), "normals_enable needs maps.normals_dev");
   int rc = apc_begin(ctx, s);
   if (rc) return rc;
   uint32_t* dc = ctx->dev_counts;
   float* ping = reinterpret_cast<float*>(ctx->buf_a);
   float* pong = reinterpret_cast<float*>(ctx->buf_b);
   int stage = 0;
+  auto last_mir = [&](void) -> const MirrorDev* {   // the stage that has just taken dst() == out_xyzi also mirrors
+    return (stage == n_stages && mir.n) ? &mir : nullptr;
+  };
   auto dst = [&](void) -> float* {  // output buffer of the stage about to run
     ++stage;
     if (stage == n_stages) return out_xyzi;
@@ -114,7 +150,7 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
                                  ctx->mask_a, nullptr, nullptr, s);
     if (rc) return rc;
     uint32_t* rows = row_out();
-    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, rows, dc + DC_STAT, 2, s, row_in);
+    rc = apc_select_nobegin(ctx, cur, n_total, dc + cur_cnt, ctx->mask_a, 0, out, rows, dc + DC_STAT, 2, s, row_in, last_mir());
     if (rc) return rc;
     row_in = rows;
     cur = out;
@@ -125,11 +161,21 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     // the select_by_mask of the radius decision also cleans the neighbour grid (one launch)
     uint32_t* rows = row_out();
     rc = apc_radius_select_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->radius_nb_points, cfg->radius_search_radius,
-                                   ctx->mask_a, out, dc + DC_RADIUS, 3, grid_in_voxel ? 1 : 0, s, row_in, rows);
+                                   ctx->mask_a, out, dc + DC_RADIUS, 3, grid_in_voxel ? 1 : 0, s, row_in, rows, last_mir());
     if (rc) return rc;
     row_in = rows;
     cur = out;
     cur_cnt = DC_RADIUS;
+  }
+  // estimate_normals (pp.py:521-530) on the cloud that enters the ground stage; without a ground
+  // stage that cloud IS the output and the normals are written in place
+  const float* nrm_in = nullptr;
+  if (has_normals && n_total) {
+    float* nrm = has_ground ? ctx->nrm_scratch : maps->normals_dev;
+    APC_REQUIRE(ctx, nrm, "normals scratch not prepared");
+    rc = apc_normals_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->normals_max_nn, cfg->normals_radius, nrm, nullptr, nullptr, s);
+    if (rc) return rc;
+    nrm_in = nrm;
   }
   if (has_ground) {
     float* out = dst();
@@ -139,7 +185,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     // non-ground points are written in order straight to `out`
     rc = apc_segment_plane_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->ground_distance_threshold, cfg->ground_ransac_n,
                                    cfg->ground_num_iterations, cfg->ground_probability, cfg->ground_seed, nullptr, plane,
-                                   nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s, row_in, rows);
+                                   nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s, row_in, rows, last_mir(), nrm_in,
+                                   nrm_in ? maps->normals_dev : nullptr);
     if (rc) return rc;
     row_in = rows;
     cur = out;
@@ -149,7 +196,7 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     k_iota<<<min(apc_div_up(n_total, 256), (uint32_t)APC_SM_COUNT * 4), 256, 0, s>>>(want_row, n_total, dc + cur_cnt);
     APC_LAUNCH_CHECK(ctx, "k_iota");
   }
-  k_pipeline_counts<<<1, 1, 0, s>>>(dc, n_total, cur_cnt, has_vox, has_stat, has_rad, has_ground, ctx->ctrl, out_counts_dev);
+  k_pipeline_counts<<<1, 1, 0, s>>>(dc, n_total, cur_cnt, has_vox, has_stat, has_rad, has_ground, ctx->ctrl, out_counts_dev, cmir);
   APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
   return APC_OK;
 }
@@ -159,6 +206,11 @@ static int prepare(apc_ctx* ctx, const apc_pipeline_cfg* cfg) {
   if (cfg->radius_enable) rc = apc_neighbors_prepare(ctx, 0);
   if (!rc && cfg->stat_enable) rc = apc_neighbors_prepare(ctx, 1);
   if (!rc && cfg->filter.dedup_mode >= APC_DEDUP_NUMPY) rc = apc_sort_prepare(ctx);
+  if (!rc && cfg->normals_enable) {
+    rc = apc_normals_prepare(ctx, cfg->normals_max_nn);
+    if (!rc && cfg->ground_enable && !ctx->nrm_scratch)
+      APC_CUDA(ctx, cudaMalloc((void**)&ctx->nrm_scratch, (size_t)ctx->max_points * 3 * sizeof(float)));
+  }
   return rc;
 }
 
@@ -182,6 +234,28 @@ extern "C" int apc_pipeline_run_maps(apc_ctx* ctx, const apc_cloud_desc* clouds,
   return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream, maps);
 }
 
+extern "C" int apc_pipeline_run_ex(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                   const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                   double* out_plane_dev, const apc_pipeline_maps* maps, const apc_out_mirror* mirror,
+                                   void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, cfg, "cfg is NULL");
+  int rc = prepare(ctx, cfg);
+  if (rc) return rc;
+  return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream, maps, mirror);
+}
+
+extern "C" int apc_pipeline_run_mirrored(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                         const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                         double* out_plane_dev, const apc_out_mirror* mirror, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  APC_REQUIRE(ctx, cfg, "cfg is NULL");
+  int rc = prepare(ctx, cfg);
+  if (rc) return rc;
+  return run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, (cudaStream_t)stream, nullptr,
+                      mirror);
+}
+
 struct apc_graph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -200,6 +274,22 @@ extern "C" int apc_graph_destroy(apc_graph* g) {
 extern "C" int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
                                           const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
                                           double* out_plane_dev, apc_graph** out_graph) {
+  return apc_graph_capture_pipeline_mirrored(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, nullptr,
+                                             out_graph);
+}
+
+extern "C" int apc_graph_capture_pipeline_mirrored(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                                   const apc_pipeline_cfg* cfg, float* out_xyzi,
+                                                   uint32_t* out_counts_dev, double* out_plane_dev,
+                                                   const apc_out_mirror* mirror, apc_graph** out_graph) {
+  return apc_graph_capture_pipeline_ex(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, nullptr, mirror,
+                                       out_graph);
+}
+
+extern "C" int apc_graph_capture_pipeline_ex(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                             const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                             double* out_plane_dev, const apc_pipeline_maps* maps,
+                                             const apc_out_mirror* mirror, apc_graph** out_graph) {
   if (!ctx) return APC_ERR_BAD_ARG;
   APC_REQUIRE(ctx, cfg && out_graph, "NULL pointer");
   *out_graph = nullptr;
@@ -211,13 +301,13 @@ extern "C" int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* cl
   if (e != cudaSuccess) { delete g; return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamCreate", e); }
   // one eager run first: lazily configured attributes (dynamic shared memory limits) are set
   // outside the capture, and argument errors surface before a capture is open
-  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream);
+  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream, maps, mirror);
   if (!rc && (e = cudaStreamSynchronize(g->capture_stream)) != cudaSuccess)
     rc = apc_set_error(ctx, APC_ERR_CUDA, "pipeline warm-up before capture", e);
   if (rc) { apc_graph_destroy(g); return rc; }
   e = cudaStreamBeginCapture(g->capture_stream, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { apc_graph_destroy(g); return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamBeginCapture", e); }
-  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream);
+  rc = run_pipeline(ctx, clouds, n_clouds, cfg, out_xyzi, out_counts_dev, out_plane_dev, g->capture_stream, maps, mirror);
   e = cudaStreamEndCapture(g->capture_stream, &g->graph);
   if (rc) { apc_graph_destroy(g); return rc; }
   if (e != cudaSuccess) { apc_graph_destroy(g); return apc_set_error(ctx, APC_ERR_CUDA, "cudaStreamEndCapture", e); }

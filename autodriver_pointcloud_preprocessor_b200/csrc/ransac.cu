@@ -4,11 +4,14 @@
 // implementation the tensor API converts to.  Contract shared with oracle/ransac.py:
 //   - hypotheses from the counter-based splitmix64 stream (or an explicit sample table),
 //     fitted with the "fast plane fit" in a fixed operation order (bit-exact vs the oracle);
-//   - one scoring pass scores all hypotheses: each CTA stages a chunk of 16 planes in shared
-//     memory and streams a tile of points past them; inlier counts and the integer error
-//     term floor(dist^2 * 2^32/thr^2) are order-independent, so warp shuffles + atomics
-//     give deterministic totals;
-//   - a single-thread epilogue applies Open3D's sequential selection / early-stop rule;
+//   - the hypotheses are generated and fitted ONCE (k_rs_hypotheses, one thread each);
+//   - one scoring pass scores all of them: each CTA stages a chunk of 16 or 20 planes in shared
+//     memory and streams tiles of points past them; inlier-ness is the float64 decision
+//     dist < thr; the error term (a tie-breaker between hypotheses with equal inlier counts
+//     only, a DEFINED deviation from Open3D's float64 rmse: DESIGN.md section 5) is the integer
+//     rint(d32^2 * float32(2^16/thr^2)) with d32 the float32 FMA distance; both are
+//     order-independent, so warp reductions + per-CTA rows give deterministic totals;
+//   - the last CTA to retire applies Open3D's sequential selection / early-stop rule;
 //   - final pass: inlier mask against the winning hypothesis + moment sums for the
 //     least-squares refit, reduced in a fixed order.
 #include <cstdlib>
@@ -123,11 +126,10 @@ __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes, co
                                            uint32_t iters, double prob, double* __restrict__ plane8,
                                            uint32_t* __restrict__ info, unsigned long long* __restrict__ scores_copy);
 
-// Hypothesis generation + scoring + selection in ONE launch.
+// Scoring + selection in one launch (the hypotheses come from k_rs_hypotheses).
 // grid = (persistent CTAs striding over point tiles, chunks of CH hypotheses).
-//   prologue  every CTA builds its own chunk of hypotheses (counter-based sampling, sample
-//             points staged through shared memory, float64 fit by CH threads); the CTAs of
-//             column 0 publish the planes for the selection and the final pass.
+//   prologue  the CTA requests its first tile of points, then stages its chunk's planes (float64
+//             and packed float32 pairs) in shared memory while those loads are in flight.
 //   scoring   a thread streams 4 points per tile past the CH planes.  The signed distance is
 //             evaluated in float32 for TWO hypotheses per instruction (FMUL2/FADD2) and compared
 //             with thr -/+ a rigorous bound on |d32 - d64|: below -> inlier, above -> outlier,
@@ -180,17 +182,54 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define RS_STAMP(k) do { } while (0)
 #endif
 
+
+// Hypothesis generation: ONE thread per hypothesis (counter-based sampling with rejection of
+// repeats, or the caller's sample table), sample points staged through shared memory, float64
+// fit.  A separate small launch so that the scoring CTAs (one per SM, half a register file each)
+// do not all repeat it: in round 1 each of the 29 CTAs of a chunk column spent 3.5 us of its
+// 15 us on the same 20 fits (profiles/r2a_rs_trace_before.txt).
+#define RS_HYP_THREADS 64
+__global__ void __launch_bounds__(RS_HYP_THREADS)
+k_rs_hypotheses(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters,
+                uint64_t seed, const int32_t* __restrict__ table, double* __restrict__ planes) {
+  __shared__ uint32_t s_idx[RS_HYP_THREADS][RS_MAX_N + 1];   // +1: rows on different banks
+  __shared__ float4 s_sp[RS_HYP_THREADS][RS_MAX_N];
+  const uint32_t P = apc_count(n_dev, n_max);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t it = blockIdx.x * RS_HYP_THREADS + tid;
+  const bool live = it < iters && P >= ransac_n;
+  if (live) {
+    if (table) {
+      for (uint32_t j = 0; j < ransac_n; ++j) s_idx[tid][j] = min((uint32_t)table[(size_t)it * ransac_n + j], P - 1);
+    } else {
+      uint32_t got = 0;
+      for (uint64_t c = 0; got < ransac_n; ++c) {
+        const uint64_t z = splitmix64_dev(seed + ((uint64_t)it << 32) + c);
+        const uint32_t cand = (uint32_t)(((z >> 32) * (uint64_t)P) >> 32);
+        bool dup = false;
+        for (uint32_t j = 0; j < got; ++j) dup |= (s_idx[tid][j] == cand);
+        if (!dup) s_idx[tid][got++] = cand;
+      }
+    }
+    for (uint32_t j = 0; j < ransac_n; ++j) s_sp[tid][j] = pts[s_idx[tid][j]];   // independent loads, all in flight
+  }
+  if (it < iters) {
+    double pl[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) rs_fit(s_sp[tid], ransac_n, pl);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) planes[4 * (size_t)it + k] = pl[k];
+  }
+}
+
 template <int CH>
-__global__ void __launch_bounds__(APC_TILE_THREADS, 2)
+__global__ void __launch_bounds__(APC_TILE_THREADS, 1)
 k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters,
-           uint64_t seed, const int32_t* __restrict__ table, double* __restrict__ planes, double thr,
+           const double* __restrict__ planes, double thr,
            unsigned long long* scores, double prob, double* __restrict__ plane8, uint32_t* __restrict__ info,
            unsigned long long* __restrict__ scores_copy, ApcCtrl* ctrl) {
   static_assert(CH % 2 == 0, "hypotheses are scored in pairs");
   __shared__ double s_pl[CH][4];
   __shared__ __align__(16) float s_pk[CH / 2][8];   // {a0,a1, b0,b1, c0,c1, d0,d1} of a pair, float32
-  __shared__ uint32_t s_idx[CH][RS_MAX_N];
-  __shared__ float4 s_sp[CH][RS_MAX_N];
   __shared__ unsigned long long s_cnt[CH], s_err[CH];   // float64-decided evaluations (rare, smem atomics)
   __shared__ uint32_t s_wcnt[APC_TILE_THREADS / 32][CH];       // per-warp totals: each warp owns its row, no atomics
   __shared__ unsigned long long s_werr[APC_TILE_THREADS / 32][CH];
@@ -206,7 +245,17 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
 #ifdef RS_TRACE
   if (threadIdx.x == 0) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_rs_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = sm; }
 #endif
-  // ---- prologue: the chunk's hypotheses ------------------------------------------------------
+  // ---- prologue: the first tile's points are requested before anything else; the chunk's planes
+  // (k_rs_hypotheses) are staged in shared memory while those loads are in flight ---------------
+  float4 nxt[APC_TILE_ITEMS];
+  {
+    const uint32_t first = blockIdx.x * APC_TILE_POINTS;
+#pragma unroll
+    for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+      const uint32_t i = first + j * APC_TILE_THREADS + tid;
+      nxt[j] = i < P ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   for (uint32_t t = tid; t < (APC_TILE_THREADS / 32) * CH; t += APC_TILE_THREADS) {
     (&s_wcnt[0][0])[t] = 0;
     (&s_werr[0][0])[t] = 0;
@@ -214,36 +263,16 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   if (tid == 0) s_qn = 0;
   if (tid < CH) {
     s_cnt[tid] = 0; s_err[tid] = 0;
-    if (tid < nh && P >= ransac_n) {
-      const uint32_t it = h0 + tid;
-      if (table) {
-        for (uint32_t j = 0; j < ransac_n; ++j) s_idx[tid][j] = min((uint32_t)table[(size_t)it * ransac_n + j], P - 1);
-      } else {
-        uint32_t got = 0;
-        for (uint64_t c = 0; got < ransac_n; ++c) {
-          const uint64_t z = splitmix64_dev(seed + ((uint64_t)it << 32) + c);
-          const uint32_t cand = (uint32_t)(((z >> 32) * (uint64_t)P) >> 32);
-          bool dup = false;
-          for (uint32_t j = 0; j < got; ++j) dup |= (s_idx[tid][j] == cand);
-          if (!dup) s_idx[tid][got++] = cand;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (uint32_t t = tid; t < CH * ransac_n; t += APC_TILE_THREADS) {   // all sample loads in flight together
-    const uint32_t h = t / ransac_n, j = t - h * ransac_n;
-    if (h < nh && P >= ransac_n) s_sp[h][j] = pts[s_idx[h][j]];
-  }
-  __syncthreads();
-  if (tid < CH) {
     double pl[4] = {0.0, 0.0, 0.0, 0.0};
-    if (tid < nh && P >= ransac_n) rs_fit(s_sp[tid], ransac_n, pl);
+    if (tid < nh) {
+      const double2 ab = *reinterpret_cast<const double2*>(planes + 4 * (size_t)(h0 + tid));
+      const double2 cd = *reinterpret_cast<const double2*>(planes + 4 * (size_t)(h0 + tid) + 2);
+      pl[0] = ab.x; pl[1] = ab.y; pl[2] = cd.x; pl[3] = cd.y;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       s_pl[tid][k] = pl[k];
       s_pk[tid >> 1][2 * k + (tid & 1)] = (float)pl[k];
-      if (blockIdx.x == 0 && tid < nh) planes[4 * (size_t)(h0 + tid) + k] = pl[k];
     }
   }
   __syncthreads();
@@ -287,9 +316,14 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   for (uint32_t first = blockIdx.x * APC_TILE_POINTS; first < P; first += gridDim.x * APC_TILE_POINTS) {
     float4 p[APC_TILE_ITEMS];
 #pragma unroll
-    for (int j = 0; j < APC_TILE_ITEMS; ++j) {   // all loads of the tile in flight before the math
-      const uint32_t i = first + j * APC_TILE_THREADS + tid;
-      p[j] = i < P ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < APC_TILE_ITEMS; ++j) p[j] = nxt[j];
+    {                                              // the next tile's loads fly under this tile's math
+      const uint32_t nfirst = first + gridDim.x * APC_TILE_POINTS;
+#pragma unroll
+      for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+        const uint32_t i = nfirst + j * APC_TILE_THREADS + tid;
+        nxt[j] = (nfirst < P && i < P) ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     float lo[APC_TILE_ITEMS], hi[APC_TILE_ITEMS];
     bool amb = false;            // one of this thread's evaluations of the tile lies inside the rounding band
@@ -381,7 +415,7 @@ __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes_in,
                                            uint32_t n_rows, uint32_t row_stride, uint32_t P, uint32_t ransac_n,
                                            uint32_t iters, double prob, double* __restrict__ plane8,
                                            uint32_t* __restrict__ info, unsigned long long* __restrict__ scores_copy) {
-  const volatile double* planes = planes_in;        // written by the column-0 CTAs of this launch
+  const double* planes = planes_in;                 // written by k_rs_hypotheses, the previous launch
   __shared__ unsigned long long s_wmax[APC_TILE_THREADS / 32];
   __shared__ unsigned long long s_carry;             // best key of all earlier chunks
   __shared__ uint32_t s_rec_it[RS_SELECT_CHUNK];     // prefix records of the current chunk, in order
@@ -414,7 +448,7 @@ __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes_in,
     if (tid < 128 && it < iters) {
       inl += s_half[tid].x;
       err += s_half[tid].y;
-      const volatile double* pl = planes + 4 * (size_t)it;
+      const double* pl = planes + 4 * (size_t)it;
       const bool valid = !(pl[0] == 0.0 && pl[1] == 0.0 && pl[2] == 0.0 && pl[3] == 0.0);
       scores_copy[2 * (size_t)it] = inl;
       scores_copy[2 * (size_t)it + 1] = err;
@@ -497,7 +531,8 @@ __global__ void __launch_bounds__(APC_TILE_THREADS)
 k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, double* __restrict__ plane8,
            uint32_t* __restrict__ info, double thr, uint8_t* __restrict__ mask, double* __restrict__ partials,
            float4* __restrict__ keep_out, uint32_t* keep_count, uint64_t* scan_state, uint32_t n_tiles, ApcCtrl* ctrl,
-           const uint32_t* __restrict__ keep_idx_in, uint32_t* __restrict__ keep_idx_out) {
+           const uint32_t* __restrict__ keep_idx_in, uint32_t* __restrict__ keep_idx_out,
+           const __grid_constant__ MirrorDev mir, const float* __restrict__ nrm_in, float* __restrict__ nrm_out) {
   __shared__ double s_red[8][10];
   __shared__ bool s_last;
   __shared__ uint32_t sm_scan[34];
@@ -537,6 +572,14 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
     for (int j = 0; j < APC_TILE_ITEMS; ++j)
       if (keep[j]) {
         keep_out[base + rank[j]] = p[j];
+        mirror_store(mir, base + rank[j], p[j]);
+        if (nrm_out) {     // the normals travel through select_by_index(inliers, invert=True) like every attribute (pp.py:542)
+          const uint32_t i = blockIdx.x * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+          const size_t o = base + rank[j];
+          nrm_out[3 * o] = nrm_in[3 * (size_t)i];
+          nrm_out[3 * o + 1] = nrm_in[3 * (size_t)i + 1];
+          nrm_out[3 * o + 2] = nrm_in[3 * (size_t)i + 2];
+        }
         if (keep_idx_out) {
           const uint32_t i = blockIdx.x * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
           keep_idx_out[base + rank[j]] = keep_idx_in ? keep_idx_in[i] : i;
@@ -597,7 +640,7 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
                               int ransac_n, int iters, double prob, uint64_t seed, const int32_t* table,
                               double* out_plane, uint8_t* out_mask, uint32_t* out_info, float* out_keep_xyzi,
                               uint32_t* out_keep_count, int scan_slot, cudaStream_t s, const uint32_t* keep_idx_in,
-                              uint32_t* keep_idx_out) {
+                              uint32_t* keep_idx_out, const MirrorDev* mir, const float* nrm_in, float* nrm_out) {
   APC_REQUIRE(ctx, out_plane && out_info && (out_mask || out_keep_xyzi), "NULL output pointer");
   APC_REQUIRE(ctx, !out_keep_xyzi || out_keep_count, "out_keep_count is NULL");
   APC_REQUIRE(ctx, prob > 0.0 && prob <= 1.0, "probability must be in (0, 1]");
@@ -631,18 +674,25 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const uint32_t gx = apc_div_up(n_tiles, apc_div_up(n_tiles, gx0));
   const dim3 grid(gx, n_chunks);
   {
+    APC_PROF(ctx, "k_rs_hypotheses", s);
+    k_rs_hypotheses<<<apc_div_up(iters, RS_HYP_THREADS), RS_HYP_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table,
+                                                                              ctx->rs_planes);
+  }
+  {
     APC_PROF(ctx, "k_rs_score", s);
     if (ch == 20)
-      k_rs_score<20><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes, thr,
+      k_rs_score<20><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr,
                                                        ctx->rs_scores, prob, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl);
     else
-      k_rs_score<16><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table, ctx->rs_planes, thr,
+      k_rs_score<16><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr,
                                                        ctx->rs_scores, prob, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl);
   }
   APC_PROF(ctx, "k_rs_final", s);
   k_rs_final<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials,
                                                   reinterpret_cast<float4*>(out_keep_xyzi), out_keep_count,
-                                                  ctx->scan_state[scan_slot], n_tiles, ctx->ctrl, keep_idx_in, keep_idx_out);
+                                                  ctx->scan_state[scan_slot], n_tiles, ctx->ctrl, keep_idx_in, keep_idx_out,
+                                                  mir && out_keep_xyzi ? *mir : MirrorDev{}, nrm_in,
+                                                  out_keep_xyzi ? nrm_out : nullptr);
   APC_LAUNCH_CHECK(ctx, "segment_plane");
   return APC_OK;
 }
@@ -658,7 +708,7 @@ extern "C" int apc_segment_plane(apc_ctx* ctx, const float* xyzi, uint32_t n_max
   if (rc) return rc;
   return apc_segment_plane_nobegin(ctx, xyzi, n_max, n_dev, distance_threshold, ransac_n, num_iterations, probability,
                                    seed, sample_table_dev, out_plane_dev, out_inlier_mask, out_info_dev, nullptr, nullptr,
-                                   4, s, nullptr, nullptr);
+                                   4, s, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 // Per-hypothesis tallies {inlier count, integer error sum} of the most recent segment_plane call.

@@ -351,27 +351,66 @@ class Context:
         out_counts = torch.zeros((8,), dtype=torch.int32, device=self.device)
         out_plane = torch.zeros((8,), dtype=torch.float64, device=self.device)
         maps = {k: self._empty((max(n_total, 1),), torch.int32) for k in ("src_idx", "p2v", "voxel_counts", "out_row")}
-        m = _capi.PipelineMaps(maps["src_idx"].data_ptr(), maps["p2v"].data_ptr(), maps["voxel_counts"].data_ptr(),
-                               maps["out_row"].data_ptr())
+        if pcfg.normals_enable:
+            maps["normals"] = self._empty((max(n_total, 1), 3), torch.float32)
+        m = make_pipeline_maps(maps)
         self._ok(lib.apc_pipeline_run_maps(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi), _ptr(out_counts),
                                            _ptr(out_plane), C.byref(m), _stream()))
         return out_xyzi, out_counts, out_plane, maps
 
-    def capture_pipeline(self, clouds, pcfg: PipelineCfg, out_xyzi, out_counts, out_plane):
+    def capture_pipeline(self, clouds, pcfg: PipelineCfg, out_xyzi, out_counts, out_plane, mirror=None, maps=None):
         """Capture the pipeline over fixed buffers into a CUDA graph; returns a handle for
-        :meth:`launch_graph`."""
+        :meth:`launch_graph`.  ``mirror``: an ``OutMirror`` from :func:`make_out_mirror` - the final
+        stage then also stores its rows / counters into the peers' buffers (``apc_out_mirror``).
+        ``maps``: dict of device tensors (``src_idx`` / ``p2v`` / ``voxel_counts`` / ``out_row`` /
+        ``normals``) the replay fills; ``normals`` is required when the config enables normals."""
         arr = (CloudDesc * len(clouds))(*clouds)
         g = C.c_void_p()
-        self._ok(lib.apc_graph_capture_pipeline(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi),
-                                                _ptr(out_counts), _ptr(out_plane), C.byref(g)))
+        m = make_pipeline_maps(maps) if maps is not None else None
+        self._ok(lib.apc_graph_capture_pipeline_ex(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi),
+                                                   _ptr(out_counts), _ptr(out_plane),
+                                                   C.byref(m) if m is not None else None,
+                                                   C.byref(mirror) if mirror is not None else None, C.byref(g)))
         self._graphs.append(g)
         return g
+
+    def pipeline_run_mirrored(self, clouds, pcfg: PipelineCfg, out_xyzi, out_counts, out_plane, mirror):
+        arr = (CloudDesc * len(clouds))(*clouds)
+        self._ok(lib.apc_pipeline_run_mirrored(self.h, arr, len(clouds), C.byref(pcfg), _ptr(out_xyzi), _ptr(out_counts),
+                                               _ptr(out_plane), C.byref(mirror), _stream()))
+        return out_xyzi, out_counts, out_plane
 
     def launch_graph(self, g):
         self._ok(lib.apc_graph_launch(self.h, g, _stream()))
 
 
-def make_pipeline_cfg(filter_cfg: FilterCfg, voxel_size=0.0, statistical=None, radius=None, ground=None) -> PipelineCfg:
+def make_pipeline_maps(maps: dict) -> "_capi.PipelineMaps":
+    """``apc_pipeline_maps`` from a dict of device tensors (missing keys = NULL)."""
+    def p(k):
+        t = maps.get(k)
+        return t.data_ptr() if t is not None else None
+    m = _capi.PipelineMaps(p("src_idx"), p("p2v"), p("voxel_counts"), p("out_row"), p("normals"))
+    m._keep_alive = maps
+    return m
+
+
+def make_out_mirror(xyzi_ptrs=(), counts_ptrs=(), multicast: bool = False) -> "_capi.OutMirror":
+    """``apc_out_mirror`` from raw device addresses (peer-mapped buffers of the other GPUs, or one NVLS
+    multicast address with ``multicast=True``).  The caller keeps the mapped tensors alive."""
+    m = _capi.OutMirror()
+    xyzi_ptrs, counts_ptrs = list(xyzi_ptrs), list(counts_ptrs)
+    if len(xyzi_ptrs) > _capi.APC_MAX_MIRRORS or len(counts_ptrs) > _capi.APC_MAX_MIRRORS:
+        raise ValueError("at most 8 mirrors")
+    m.n_xyzi, m.xyzi_multicast, m.n_counts = len(xyzi_ptrs), int(bool(multicast)), len(counts_ptrs)
+    for i, p in enumerate(xyzi_ptrs):
+        m.xyzi_dev[i] = int(p)
+    for i, p in enumerate(counts_ptrs):
+        m.counts_dev[i] = int(p)
+    return m
+
+
+def make_pipeline_cfg(filter_cfg: FilterCfg, voxel_size=0.0, statistical=None, radius=None, ground=None,
+                      normals=None) -> PipelineCfg:
     p = PipelineCfg()
     p.filter = filter_cfg
     p.voxel_size = float(voxel_size or 0.0)
@@ -388,4 +427,7 @@ def make_pipeline_cfg(filter_cfg: FilterCfg, voxel_size=0.0, statistical=None, r
         p.ground_num_iterations = int(ground["num_iterations"])
         p.ground_probability = float(ground["probability"])
         p.ground_seed = int(ground.get("seed", 0))
+    if normals:
+        p.normals_enable, p.normals_max_nn = 1, int(normals["max_nn"])
+        p.normals_radius = float(normals["radius"])
     return p

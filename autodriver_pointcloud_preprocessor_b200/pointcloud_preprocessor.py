@@ -295,10 +295,10 @@ class PointcloudPreprocessorNode(Node):
             return True
         if self.fused_pipeline is False or str(self.fused_pipeline).lower() in ('false', '0', 'off'):
             return False
-        # 'auto': the fused pipeline carries x, y, z, intensity itself and ring / time / return_type
-        # through its index maps; colour clouds take the staged carrier path
-        m = self.pointcloud_metadata or {}
-        return not m.get('has_rgb')
+        # 'auto': the fused pipeline carries x, y, z, intensity itself, estimates the normals between the
+        # outlier and the ground stage, and ring / time / return_type / rgb travel through its index maps.
+        # Only parameter values beyond the kernels' caps take the staged carrier path.
+        return not (self.estimate_normals and self.estimate_normals_max_neighbors > 64)
 
     # ------------------------------------------------------------------------------------------------
     def extract_pointcloud(self, ros_cloud):
@@ -413,11 +413,15 @@ class PointcloudPreprocessorNode(Node):
             ground=dict(distance_threshold=self.remove_ground_distance_threshold,
                         ransac_n=self.remove_ground_ransac_number, num_iterations=self.remove_ground_num_iterations,
                         probability=self.remove_ground_probability, seed=self.remove_ground_seed)
-            if (self.remove_ground and not self.estimate_normals) else None)
+            if self.remove_ground else None,
+            # estimate_normals is ON by default (pp.py:176) and sits between the outlier and the ground stage
+            # (pp.py:521-543): one launch chain, the normals travel through the ground selection
+            normals=dict(radius=self.estimate_normals_search_radius, max_nn=self.estimate_normals_max_neighbors)
+            if self.estimate_normals else None)
         meta = self.pointcloud_metadata
-        extra = [k for k in ('ring', 'time', 'return_type') if meta.get(f'has_{k}')]
+        extra = [k for k in ('ring', 'time', 'return_type', 'rgb') if meta.get(f'has_{k}')]
         maps = None
-        if extra:
+        if extra or self.estimate_normals:
             out, counts, plane, maps = ctx.pipeline_run_maps([desc], pcfg)
         else:
             out, counts, plane = ctx.pipeline_run([desc], pcfg)
@@ -429,30 +433,47 @@ class PointcloudPreprocessorNode(Node):
         cloud.point['positions'] = pos if self.use_gpu else pos.cpu()
         if inten is not None:
             cloud.point['intensity'] = (inten if self.use_gpu else inten.cpu()).reshape(-1, 1)
-        if maps is not None:
+        if extra:
             # attributes the kernels do not touch: cut from the message bytes, gathered with the front
             # end's surviving indices, averaged per voxel "in float32 then cast back" like Open3D does
             # for every attribute (pp.py:511), gathered with the rows that survived the later stages
             m_filt, n_vox = int(c[_capi.CNT_FILTERED]), int(c[_capi.CNT_VOXELS])
             rows = raw[:n * msg.point_step].view(n, msg.point_step)
             by_name = {f.name: f for f in msg.fields}
-            ref_dtype = {'ring': torch.uint16, 'time': torch.float64, 'return_type': torch.uint8}   # utils.py:120-131
-            for key in extra:
-                col = raw_column(rows, by_name[meta[f'{key}_field_name']]).to(ref_dtype[key])
-                a = ctx.gather(col, maps['src_idx'], m_filt)
+            ref_dtype = {'ring': torch.uint16, 'time': torch.float64, 'return_type': torch.uint8,
+                         'rgb': torch.float32}                                                    # utils.py:110-131, pp.py:429-431
+
+            def carry(col):
+                """one attribute column (input order) -> the same column of the output cloud"""
+                a = ctx.gather(col.contiguous(), maps['src_idx'], m_filt)
                 if self.voxel_size > 0.0:
                     mean = ctx.voxel_mean_attr(a.to(torch.float32).contiguous(), maps['p2v'],
                                                counts[_capi.CNT_VOXELS:_capi.CNT_VOXELS + 1], m_filt)[:n_vox]
-                    a = mean.to(ref_dtype[key])
-                a = ctx.gather(a.contiguous(), maps['out_row'], n_out)
+                    a = mean.to(col.dtype)
+                return ctx.gather(a.contiguous(), maps['out_row'], n_out)
+
+            for key in extra:
+                if key == 'rgb':
+                    # three uint8 channels (separate r/g/b fields, or one packed float32: utils.py:110-119,
+                    # 324-345), scaled to float32 [0, 1] like pp.py:429-431, each carried like any attribute
+                    if {"r", "g", "b"}.issubset(by_name):
+                        chans = [raw_column(rows, by_name[ch]).to(torch.uint8) for ch in ("r", "g", "b")]
+                    else:
+                        packed = raw_column(rows, by_name["rgb"]).view(torch.int32)
+                        chans = [((packed >> sh) & 0xFF).to(torch.uint8) for sh in (16, 8, 0)]
+                    a = torch.stack([carry(ch.to(torch.float32) / 255.0) for ch in chans], 1)
+                    cloud.point['rgb'] = a if self.use_gpu else a.cpu()
+                    continue
+                a = carry(raw_column(rows, by_name[meta[f'{key}_field_name']]).to(ref_dtype[key]))
                 cloud.point[key] = (a if self.use_gpu else a.cpu()).reshape(-1, 1)
+        if self.estimate_normals and maps is not None:
+            nrm = maps['normals'][:n_out]
+            cloud.point['normals'] = nrm if self.use_gpu else nrm.cpu()
+            self.pointcloud_metadata['has_normals'] = True
         self.o3d_pointcloud = cloud
         self._fused_xyzi = (out[:n_out], cloud)       # prepare_pointcloud repacks straight from this
         self.last_counts = c
         self.last_plane = plane.cpu().numpy()
-        if self.estimate_normals:
-            # normals come before the ground stage (pp.py:521-543) and travel through its selection
-            self._normals_and_ground()
         return self.o3d_pointcloud
 
     def _normals_and_ground(self):

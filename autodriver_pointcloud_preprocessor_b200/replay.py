@@ -7,9 +7,11 @@ lane's kernels run, another lane's H2D / D2H copies and small latency-bound kern
 
 Scans are independent units (the reference keeps no cross-frame state besides the cached
 static TF, pp.py:706), so multi-GPU is frame-parallel with no collective on the per-scan
-path; ``shard_frames`` deals contiguous blocks of frames to ranks and ``gather_outputs``
-all-gathers the per-GPU results (NCCL over NVLink on the GPU box, gloo in the CPU tests) for
-the batched PCAP-replay configuration only.
+path; ``shard_frames`` deals contiguous blocks of frames to ranks.  The batched PCAP-replay
+configuration ends with every GPU holding every GPU's output: ``PeerSlabs`` fuses that exchange
+into the pipeline's final kernel (peer stores over NVLink while the kernels run);
+``gather_outputs`` is the plain all-gather (NCCL on the GPU box when symmetric memory is not
+available, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -47,42 +49,61 @@ def gather_outputs(send: torch.Tensor, counts: torch.Tensor, group=None):
     return recv, all_counts
 
 
-class PeerGather:
-    """The same all-gather by peer-to-peer copies over NVLink, double buffered: every lane stages a
-    frame's output rows straight into this rank's slot of a symmetric buffer (``slot(parity)``), and
-    ``gather(parity)`` pushes that slot into the same slot of every peer's buffer with the copy
-    engines, bracketed by two signal-pad barriers - while the next step fills the other parity.
-    NCCL's all-gather kernels take SMs away from the scan kernels that run underneath and need a
-    staging copy on the compute stream; copy-engine traffic needs neither.  The per-frame counts
-    stay on NCCL.
+class PeerSlabs:
+    """Output slabs of the exchange that is FUSED into the pipeline's final stage (``apc_out_mirror``).
 
-    Needs ``torch.distributed._symmetric_memory`` and peer access between the GPUs of the node;
-    construct inside ``try`` and fall back to :func:`gather_outputs` when it raises.
-    """
+    Every rank owns ``[parity][source rank][frame][rows][4]`` float32 plus ``[...][8]`` int32 counter
+    slabs in symmetric memory.  A frame's graph writes its surviving rows into this rank's own block
+    of the LOCAL slab and, with the same store loop, into the same block of every PEER's slab over
+    NVLink (peer-mapped pointers, or one NVLS multicast address when the fabric offers it): no
+    gather pass, no staging copy, no padding on the wire - only the rows that exist travel, while
+    the kernels run.  ``barrier()`` (signal pads, on the current stream) separates "all ranks have
+    finished writing this parity" from its readers / its next reuse.
 
-    def __init__(self, slab_shape, dtype, device, group=None):
+    Needs ``torch.distributed._symmetric_memory`` and peer access between the GPUs of the node."""
+
+    def __init__(self, n_frames: int, rows: int, device, group=None, parities: int = 2, multicast: bool | None = None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         group = dist.group.WORLD if group is None else group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.buf = symm.empty((2, self.world) + tuple(slab_shape), dtype=dtype, device=device)
+        self.n_frames, self.rows, self.parities = int(n_frames), int(rows), int(parities)
+        shape = (self.parities, self.world, self.n_frames, self.rows, 4)
+        cshape = (self.parities, self.world, self.n_frames, 8)
+        self.buf = symm.empty(shape, dtype=torch.float32, device=device)
+        self.cnt = symm.empty(cshape, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.cnt.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
-        self.peers = [self.hdl.get_buffer(p, tuple(self.buf.shape), dtype) for p in range(self.world)]
+        self.hdl_c = symm.rendezvous(self.cnt, group)
+        self.peer_buf = [self.hdl.get_buffer(p, shape, torch.float32) for p in range(self.world)]
+        self.peer_cnt = [self.hdl_c.get_buffer(p, cshape, torch.int32) for p in range(self.world)]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast_base = mc if (multicast is None or multicast) else 0
+        if multicast and not mc:
+            raise RuntimeError("NVLS multicast requested but the symmetric-memory handle has no multicast mapping")
 
-    def slot(self, parity: int) -> torch.Tensor:
-        """This rank's [F, rows, 4] staging slab of the given parity (local memory)."""
-        return self.buf[parity][self.rank]
+    def local_out(self, parity: int, f: int):
+        """(rows [rows, 4], counters [8]) of frame ``f`` in this rank's own block of the local slab."""
+        return self.buf[parity][self.rank][f], self.cnt[parity][self.rank][f]
 
-    def gather(self, parity: int) -> torch.Tensor:
-        """Issue on the current stream; returns the local [G, F, rows, 4] buffer of that parity
-        (complete, in stream order, once this call's second barrier has passed)."""
-        self.hdl.barrier(channel=0)                       # every peer is done with this parity's previous contents
-        src = self.buf[parity][self.rank]
-        for k in range(1, self.world):                    # rank+1, rank+2, ...: no hot spot
-            p = (self.rank + k) % self.world
-            self.peers[p][parity][self.rank].copy_(src, non_blocking=True)
-        self.hdl.barrier(channel=1)                       # every rank's slabs have landed everywhere
-        return self.buf[parity]
+    def mirror(self, parity: int, f: int):
+        """``apc_out_mirror`` addressing the same block in every peer's slab."""
+        peers = [(self.rank + k) % self.world for k in range(1, self.world)]     # rank+1, rank+2, ...: no hot spot
+        cnts = [self.peer_cnt[p][parity][self.rank][f].data_ptr() for p in peers]
+        if self.multicast_base:
+            # the multicast mapping covers every rank's buffer at the same offset (this rank's included:
+            # its own copy is then written twice, which is harmless)
+            off = self.buf[parity][self.rank][f].data_ptr() - self.buf.data_ptr()
+            return engine.make_out_mirror([self.multicast_base + off], cnts, multicast=True)
+        return engine.make_out_mirror([self.peer_buf[p][parity][self.rank][f].data_ptr() for p in peers], cnts)
+
+    def barrier(self, channel: int = 0):
+        self.hdl.barrier(channel=channel)
+
+    def frame(self, parity: int, src_rank: int, f: int):
+        """Received (or own) rows and counters of frame ``f`` of ``src_rank``."""
+        return self.buf[parity][src_rank][f], self.cnt[parity][src_rank][f]
 
 
 class _Lane:
@@ -213,28 +234,37 @@ class ScanPipeline:
 
     # ---- device resident: inputs already in HBM -----------------------------------------------------
     def prepare_resident(self, pool: torch.Tensor, arena: torch.Tensor | None = None,
-                         counts_arena: torch.Tensor | None = None):
+                         counts_arena: torch.Tensor | None = None, slabs: "PeerSlabs | None" = None):
         """Capture one graph per pool frame (``pool`` [F, frame_bytes] uint8 on the device) so
         replaying reads each frame in place.  With ``arena`` [F, n_points, 4] / ``counts_arena``
-        [F, 8] every frame writes its own output slot (needed for the multi-GPU gather)."""
+        [F, 8] every frame writes its own output slot.  With ``slabs`` (multi-GPU) one graph per
+        frame and slab parity is captured whose final stage writes the frame's rows and counters
+        into this rank's block of the local slab AND of every peer's slab (the fused exchange)."""
         self._pool = pool
         self._resident_out = {}
         S = len(self.lanes)
         for f in range(pool.shape[0]):
             ln = self.lanes[f % S]
             desc = engine.make_cloud_desc(self.fields, self.point_step, self.n_points, pool[f])
+            if slabs is not None:
+                for parity in range(slabs.parities):
+                    out, cnt = slabs.local_out(parity, f)
+                    ln.resident_graphs[(f, parity)] = ln.ctx.capture_pipeline([desc], self.pcfg, out, cnt, ln.d_plane,
+                                                                              mirror=slabs.mirror(parity, f))
+                continue
             out = arena[f] if arena is not None else ln.d_out
             cnt = counts_arena[f] if counts_arena is not None else ln.d_counts
             self._resident_out[f] = out
             ln.resident_graphs[f] = ln.ctx.capture_pipeline([desc], self.pcfg, out, cnt, ln.d_plane)
         torch.cuda.synchronize(self.device)
 
-    def run_resident(self, frame_ids, main_stream=None, stage_to: torch.Tensor | None = None):
+    def run_resident(self, frame_ids, main_stream=None, parity: int | None = None,
+                     stage_to: torch.Tensor | None = None):
         """Replay the captured graphs for ``frame_ids`` across the lanes.  The caller's current
         stream is the fork/join point, so CUDA events recorded on it bracket the whole batch.
-        ``stage_to`` [F, rows, 4]: each lane also copies the first ``rows`` rows of the frame's
-        output into ``stage_to[f]`` right behind the frame's graph (a copy-engine copy on the lane's
-        own stream), e.g. into the slab the multi-GPU gather sends."""
+        ``parity``: which slab parity's graphs to replay (graphs captured with ``slabs``).
+        ``stage_to`` [F, rows, 4] (NCCL fall-back only): each lane copies the first ``rows`` rows of
+        the frame's output into ``stage_to[f]`` right behind the frame's graph."""
         main = torch.cuda.current_stream(self.device) if main_stream is None else main_stream
         S = len(self.lanes)
         fork = torch.cuda.Event()
@@ -244,7 +274,7 @@ class ScanPipeline:
         for f in frame_ids:
             ln = self.lanes[f % S]
             with torch.cuda.stream(ln.stream):
-                ln.ctx.launch_graph(ln.resident_graphs[f])
+                ln.ctx.launch_graph(ln.resident_graphs[f if parity is None else (f, parity)])
                 if stage_to is not None:
                     stage_to[f].copy_(self._resident_out[f][:stage_to.shape[1]], non_blocking=True)
         for ln in self.lanes:

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define APC_VERSION 110 /* 0.1.1: + apc_unique_rows, apc_estimate_normals, apc_pipeline_run_maps, sorted dedup modes */
+#define APC_VERSION 120 /* 0.1.2: + mirrored outputs (multi-GPU exchange fused into the final stage) */
 
 typedef enum apc_status {
   APC_OK = 0,
@@ -291,6 +291,10 @@ typedef struct apc_pipeline_cfg {
   int32_t ground_num_iterations;
   double ground_probability;
   uint64_t ground_seed;
+  int32_t normals_enable;      /* estimate_normals (pp.py:521-530, on by default pp.py:176): runs on the cloud that
+                                  enters the ground stage; the normals travel through its selection (pp.py:542) */
+  int32_t normals_max_nn;      /* 1..64 */
+  double normals_radius;
 } apc_pipeline_cfg;
 
 /* counters mirrored to the host after a pipeline run (index into out_counts_dev uint32[8]) */
@@ -312,16 +316,46 @@ int apc_pipeline_run(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clou
  *   p2v_dev           int32:  voxel row of every such point (voxel stage enabled)
  *   voxel_counts_dev  uint32: points per voxel row
  *   out_row_dev       uint32: for every output point, its row in the cloud after the voxel stage
- *                             (after the front end when the voxel stage is off) */
+ *                             (after the front end when the voxel stage is off)
+ *   normals_dev       float32[3*]: with cfg.normals_enable, the normal of every output point (required then) */
 typedef struct apc_pipeline_maps {
   uint32_t* src_idx_dev;
   int32_t* p2v_dev;
   uint32_t* voxel_counts_dev;
   uint32_t* out_row_dev;
+  float* normals_dev;           /* float32[3 * sum n_points]: normal of every OUTPUT point (cfg.normals_enable) */
 } apc_pipeline_maps;
 int apc_pipeline_run_maps(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
                           const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
                           double* out_plane_dev, const apc_pipeline_maps* maps, void* stream);
+
+/* Multi-GPU exchange fused into the pipeline's final stage (batched replay configuration, SURVEY.md
+ * section 8e: "NCCL all-gather of per-GPU outputs"): besides out_xyzi / out_counts_dev, the kernel
+ * that writes the final cloud stores every surviving row - and k_pipeline_counts the 8 counters -
+ * into up to APC_MAX_MIRRORS further buffers, typically the same slot of every peer GPU's slab,
+ * mapped into this process (CUDA peer access / symmetric memory).  Only the real rows cross NVLink.
+ * With xyzi_multicast != 0, xyzi_dev[0] is an NVLS multicast address covering all peers (one
+ * multimem.st per row, replicated by the switch).  The final stage must be a selection
+ * (statistical / radius outlier removal or ground removal): APC_ERR_BAD_ARG otherwise.  The rows are
+ * complete on the peers when the launching stream has passed the launch (follow with a barrier
+ * between the ranks before the peers read them). */
+#define APC_MAX_MIRRORS 8
+typedef struct apc_out_mirror {
+  uint32_t n_xyzi;
+  int32_t xyzi_multicast;
+  float* xyzi_dev[APC_MAX_MIRRORS];        /* float4[sum n_points] each */
+  uint32_t n_counts;
+  uint32_t* counts_dev[APC_MAX_MIRRORS];   /* uint32[8] each (APC_CNT_*) */
+} apc_out_mirror;
+int apc_pipeline_run_mirrored(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                              const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                              double* out_plane_dev, const apc_out_mirror* mirror, void* stream);
+
+/* Most general form: index maps / normals (maps may be NULL) and mirrored outputs (mirror may be NULL). */
+int apc_pipeline_run_ex(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                        const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                        double* out_plane_dev, const apc_pipeline_maps* maps, const apc_out_mirror* mirror,
+                        void* stream);
 
 /* The same pipeline captured once into a CUDA graph (fixed buffers, sizes and config) and
  * replayed per scan: one launch per frame instead of ~25.  The per-frame input is whatever
@@ -331,6 +365,15 @@ int apc_graph_capture_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint3
                                const apc_pipeline_cfg* cfg, float* out_xyzi,
                                uint32_t* out_counts_dev, double* out_plane_dev,
                                apc_graph** out_graph);
+/* as apc_graph_capture_pipeline, with mirrored outputs (mirror may be NULL) */
+int apc_graph_capture_pipeline_mirrored(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                        const apc_pipeline_cfg* cfg, float* out_xyzi,
+                                        uint32_t* out_counts_dev, double* out_plane_dev,
+                                        const apc_out_mirror* mirror, apc_graph** out_graph);
+int apc_graph_capture_pipeline_ex(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_clouds,
+                                  const apc_pipeline_cfg* cfg, float* out_xyzi, uint32_t* out_counts_dev,
+                                  double* out_plane_dev, const apc_pipeline_maps* maps,
+                                  const apc_out_mirror* mirror, apc_graph** out_graph);
 int apc_graph_launch(apc_ctx* ctx, apc_graph* graph, void* stream);
 /* number of kernel nodes one replay of the graph launches (>= 0) or a negative apc_status */
 int apc_graph_kernel_count(const apc_graph* graph);

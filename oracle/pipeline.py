@@ -110,9 +110,9 @@ def preprocess(cloud_msgs, cfg, per_sensor_transforms=None):
         m = outliers.radius_mask(pos, r["nb_points"], r["radius"])
         out["radius_mask"] = m
         pos, inten = pos[m], inten[m]
-    nrm = None
+    nrm = ncov = None
     if cfg.get("normals"):
-        nrm, out["normal_counts"], _ = normals.estimate_normals(pos, cfg["normals"]["radius"], cfg["normals"]["max_nn"])
+        nrm, out["normal_counts"], ncov = normals.estimate_normals(pos, cfg["normals"]["radius"], cfg["normals"]["max_nn"])
     if cfg.get("ground"):
         g = cfg["ground"]
         plane, inl, info = ransac.segment_plane(pos, g["distance_threshold"], g["ransac_n"],
@@ -122,7 +122,8 @@ def preprocess(cloud_msgs, cfg, per_sensor_transforms=None):
         keep[inl] = False
         pos, inten = pos[keep], inten[keep]
         nrm = nrm[keep] if nrm is not None else None
+        ncov = ncov[keep] if ncov is not None else None
     if nrm is not None:
-        out["normals"] = nrm
+        out["normals"], out["normal_cov"] = nrm, ncov
     out["positions"], out["intensity"] = pos, inten
     return out

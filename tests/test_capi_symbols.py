@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in apc.h but not exported"
     assert sorted(_capi.SYMBOLS) == names          # the ctypes binding covers the whole header
-    assert lib.apc_version() == 110                 # APC_VERSION in apc.h
+    assert lib.apc_version() == 120                 # APC_VERSION in apc.h
 
 
 def test_struct_layouts_match_header():
@@ -32,8 +32,8 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "apc.h"
-int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(apc_field), sizeof(apc_cloud_desc), sizeof(apc_filter_cfg),
-  sizeof(apc_out_field), sizeof(apc_pipeline_cfg)); return 0;}
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(apc_field), sizeof(apc_cloud_desc), sizeof(apc_filter_cfg),
+  sizeof(apc_out_field), sizeof(apc_pipeline_cfg), sizeof(apc_out_mirror), sizeof(apc_pipeline_maps)); return 0;}
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -41,7 +41,8 @@ int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(apc_field), sizeof(apc_clo
         exe = os.path.join(d, "t")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    got = [ctypes.sizeof(t) for t in (_capi.Field, _capi.CloudDesc, _capi.FilterCfg, _capi.OutField, _capi.PipelineCfg)]
+    got = [ctypes.sizeof(t) for t in (_capi.Field, _capi.CloudDesc, _capi.FilterCfg, _capi.OutField, _capi.PipelineCfg,
+                                       _capi.OutMirror, _capi.PipelineMaps)]
     assert got == sizes
 
 

@@ -132,3 +132,54 @@ def test_carrier_normals_and_transform(env):
     # normals travel through selections like any attribute
     sub = pcd.select_by_index(o3d.Tensor(torch.arange(0, p.shape[0], 3).cuda()))
     assert np.array_equal(sub.point.normals.cpu().numpy(), pcd.point.normals.cpu().numpy()[::3])
+
+
+@pytest.mark.parametrize("with_ground", [False, True])
+def test_reference_default_parameter_set_as_one_graph(env, with_ground):
+    """The reference's DEFAULT stage set - duplicate removal + non-finite + crop + 0.01 m voxels +
+    estimate_normals(0.1, 30) (pp.py:165-178) - captured as ONE CUDA graph (normals are a stage of
+    ``apc_pipeline_cfg``), optionally followed by ground removal, through whose selection the normals
+    travel (pp.py:542).  Positions bit-exact, normals bounded as in ``check_normals``."""
+    from oracle import pipeline as opipe
+    ctx, engine, capi, synth = env["ctx"], env["engine"], env["capi"], env["synth"]
+    msg = synth.pack_cloud(synth.lidar_scan(seed=31, n_beams=32, n_az=1024), "xyzirt22")
+    n = msg.width
+    data = torch.frombuffer(bytearray(msg.data), dtype=torch.uint8).cuda()
+    desc = engine.make_cloud_desc(msg.fields, msg.point_step, n, data)
+    crop = dict(min=[-60.0, -60.0, -20.0], max=[60.0, 60.0, 20.0], invert=False, mode=capi.CROP_OPEN3D)
+    fcfg = engine.make_filter_cfg(skip_nans=True, dedup_mode=capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True, crop=crop)
+    # 0.01 m voxels keep nearly every point of a sparse scan; the default radius 0.1 then finds few
+    # neighbours - exactly what the reference computes; a second case uses a denser 0.1 / 0.5 setting
+    ground = dict(distance_threshold=0.2, ransac_n=5, num_iterations=50, probability=0.99, seed=11) if with_ground else None
+    for voxel_size, nrm_cfg in ((0.01, dict(radius=0.1, max_nn=30)), (0.1, dict(radius=0.5, max_nn=30))):
+        pcfg = engine.make_pipeline_cfg(fcfg, voxel_size=voxel_size, ground=ground, normals=nrm_cfg)
+        out = torch.zeros((n, 4), device="cuda")
+        cnt = torch.zeros(8, dtype=torch.int32, device="cuda")
+        plane = torch.zeros(8, dtype=torch.float64, device="cuda")
+        maps = {"normals": torch.zeros((n, 3), device="cuda")}
+        g = ctx.capture_pipeline([desc], pcfg, out, cnt, plane, maps=maps)
+        cfg = opipe.default_config()
+        cfg.update(crop=crop, voxel_size=voxel_size, ground=ground, normals=nrm_cfg)
+        ref = opipe.preprocess(msg, cfg)
+        for _ in range(2):                                            # the graph replays cleanly
+            out.zero_()
+            maps["normals"].zero_()
+            ctx.launch_graph(g)
+            ctx.check()
+            c = cnt.cpu().numpy()
+            k = int(c[capi.CNT_OUTPUT])
+            assert c[capi.CNT_STATUS] == 0 and k == ref["positions"].shape[0]
+            assert np.array_equal(out[:k].cpu().numpy()[:, :3].view(np.uint32), ref["positions"].view(np.uint32))
+            got = maps["normals"][:k].cpu().numpy()
+            few = ref["normal_counts"] < 3
+            if with_ground:
+                keep = np.ones(few.shape[0], dtype=bool)
+                keep[ref["ground_inliers"]] = False
+                few = few[keep]
+            assert np.array_equal(got[few], np.tile(np.array([0, 0, 1], np.float32), (int(few.sum()), 1)))
+            check_normals(got[~few], ref["normal_cov"][~few], ref["normals"][~few])
+        # eager run through apc_pipeline_run_maps gives the same bits as the graph
+        out2, cnt2, _, maps2 = ctx.pipeline_run_maps([desc], pcfg)
+        ctx.check()
+        assert np.array_equal(cnt2.cpu().numpy(), c)
+        assert np.array_equal(maps2["normals"][:k].cpu().numpy().view(np.uint32), got.view(np.uint32))
