@@ -94,6 +94,7 @@ def _load():
         "apc_pack_xyzi": [vp, vp, vp, u32, vp, vp],
         "apc_split_xyzi": [vp, vp, u32, vp, vp, vp, vp],
         "apc_voxel_downsample": [vp, vp, u32, vp, C.c_float, vp, vp, vp, vp, vp],
+        "apc_voxel_downsample_sorted": [vp, vp, u32, vp, C.c_float, vp, vp, vp, vp],
         "apc_voxel_mean_attr": [vp, vp, vp, u32, vp, vp, vp, vp],
         "apc_radius_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp],
         "apc_statistical_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp, vp],
@@ -137,7 +138,7 @@ lib = _load()
 SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "apc_version",
            "apc_ctx_max_points", "apc_frontend", "apc_unpack", "apc_transform", "apc_crop_mask",
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
-           "apc_voxel_downsample", "apc_voxel_mean_attr", "apc_radius_outliers",
+           "apc_voxel_downsample", "apc_voxel_downsample_sorted", "apc_voxel_mean_attr", "apc_radius_outliers",
            "apc_statistical_outliers", "apc_estimate_normals", "apc_segment_plane", "apc_segment_plane_scores", "apc_repack", "apc_pipeline_run", "apc_pipeline_run_maps",
            "apc_pipeline_run_mirrored", "apc_pipeline_run_ex", "apc_graph_capture_pipeline_ex",
            "apc_graph_capture_pipeline", "apc_graph_capture_pipeline_mirrored",

@@ -89,6 +89,7 @@ struct apc_ctx {
   uint64_t* sort_status = nullptr;  // [sort tiles][256] look-back words
   uint32_t* sort_idx = nullptr;     // [max_points] first-index / inverse list of the pipeline's sort modes
   float* nrm_scratch = nullptr;     // [3 * max_points] normals of the cloud entering the ground stage (pipeline), on first use
+  struct NeighborScratch* neighbors = nullptr;   // neighbour grids + KNN scratch (neighbors.cu), on first use
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.

@@ -603,26 +603,15 @@ struct NeighborScratch {
   double* stats = nullptr;
   double* cov = nullptr;            // [max_points][9] covariances between k_normals_cov and k_normals_eigen
 };
-// one scratch set per context, keyed by pointer (contexts are few; freed at process exit)
-#include <map>
-#include <mutex>
-static std::map<apc_ctx*, NeighborScratch*> g_scratch;
-static std::mutex g_scratch_mu;
-
+// one scratch set per context, owned by the context (created on first use, freed by apc_ctx_destroy)
 static NeighborScratch* scratch_of(apc_ctx* ctx) {
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  auto it = g_scratch.find(ctx);
-  if (it != g_scratch.end()) return it->second;
-  auto* s = new NeighborScratch();
-  g_scratch[ctx] = s;
-  return s;
+  if (!ctx->neighbors) ctx->neighbors = new NeighborScratch();
+  return ctx->neighbors;
 }
 
 void apc_neighbors_release(apc_ctx* ctx) {
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  auto it = g_scratch.find(ctx);
-  if (it == g_scratch.end()) return;
-  NeighborScratch* s = it->second;
+  NeighborScratch* s = ctx->neighbors;
+  if (!s) return;
   for (auto& g : s->grid) {
     void* ptrs[] = {g.d.slots, g.d.slot, g.d.rank, g.d.sorted, g.d.cell};
     for (void* p : ptrs)
@@ -632,7 +621,7 @@ void apc_neighbors_release(apc_ctx* ctx) {
   if (s->stats) cudaFree(s->stats);
   if (s->cov) cudaFree(s->cov);
   delete s;
-  g_scratch.erase(it);
+  ctx->neighbors = nullptr;
 }
 
 // Allocates (once) the grid for `levels` levels; must run outside stream capture.

@@ -3,6 +3,7 @@
 // counters so that no stage waits for the host, plus CUDA-graph capture / replay of the
 // whole chain (one launch per scan).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "apc_grid.cuh"
@@ -54,6 +55,12 @@ __global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t
 #pragma unroll
     for (int k = 0; k < 8; ++k) mir.out[m][k] = c[k];
   APC_STAMP(0, 0);
+}
+
+// A/B probe (APC_DUMMY_KERNELS=k): k empty launches per scan, to separate "saturated throughput is set
+// by the number of launches" from "... by the work inside them" (profiles/).
+__global__ void k_nop(const ApcCtrl* ctrl) {
+  if (threadIdx.x == 99 && ctrl->epoch == 0xffffffffu) printf("never");
 }
 
 __global__ void k_iota(uint32_t* out, uint32_t n_max, const uint32_t* n_dev) {
@@ -123,6 +130,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, maps ? maps->src_idx_dev : nullptr, nullptr,
                             dc + DC_FILTERED, 0, s);
   if (rc) return rc;
+  static const int n_dummy = []() { const char* e = getenv("APC_DUMMY_KERNELS"); return e ? atoi(e) : 0; }();
+  for (int k = 0; k < n_dummy; ++k) k_nop<<<1, 32, 0, s>>>(ctx->ctrl);
   // voxel -> radius with nothing in between: the voxel stage inserts its centroids into the radius
   // grid as it writes them (one launch and one pass over the centroids less)
   static const bool fuse_grid = getenv("APC_NO_GRID_FUSION") == nullptr;   // A/B knob for profiles/

@@ -39,10 +39,22 @@ __device__ __forceinline__ uint32_t sort_digit(const uint4& r, uint32_t pass) {
   return (c >> ((pass & 3u) * 8u)) & 255u;
 }
 
+// voxel index of one coordinate, biased to [0, 2^21): the same arithmetic as voxel.cu voxel_key
+__device__ __forceinline__ bool sort_voxel_coord(float v, float vs, uint32_t& u) {
+  if (!(fabsf(v) < 65536.0f)) return false;
+  const float q = floorf(__fdiv_rn(v, vs));
+  if (!(q >= -1048576.0f && q < 1048576.0f)) return false;
+  u = (uint32_t)((int32_t)q + 1048576);
+  return true;
+}
+
 // ---- keys + the twelve digit histograms in one pass over the points ---------------------------
+// VOXEL = false: order-preserving float keys of x, y, z (duplicate removal, numpy / torch back ends)
+// VOXEL = true:  biased voxel indices floor(x / voxel_size) (sort-based voxel grid, apc_voxel_downsample_sorted)
+template <bool VOXEL>
 __global__ void __launch_bounds__(256)
 k_sort_keys(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint4* __restrict__ keys,
-            uint32_t* __restrict__ hist) {
+            uint32_t* __restrict__ hist, float vs, ApcCtrl* ctrl) {
   __shared__ uint32_t sh[SORT_PASSES * 256];
   for (uint32_t i = threadIdx.x; i < SORT_PASSES * 256; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
@@ -52,7 +64,13 @@ k_sort_keys(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_de
     const uint32_t vm = __ballot_sync(0xffffffffu, i < n);
     if (i >= n) continue;
     const float4 p = pts[i];
-    const uint4 r = make_uint4(sort_key_f32(p.x), sort_key_f32(p.y), sort_key_f32(p.z), i);
+    uint4 r = make_uint4(sort_key_f32(p.x), sort_key_f32(p.y), sort_key_f32(p.z), i);
+    if (VOXEL) {
+      uint32_t ux = 0x1fffffu, uy = 0x1fffffu, uz = 0x1fffffu;
+      if (!(sort_voxel_coord(p.x, vs, ux) && sort_voxel_coord(p.y, vs, uy) && sort_voxel_coord(p.z, vs, uz)))
+        atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+      r = make_uint4(ux, uy, uz, i);
+    }
     keys[i] = r;
 #pragma unroll
     for (uint32_t pass = 0; pass < SORT_PASSES; ++pass) {
@@ -262,7 +280,7 @@ int apc_unique_rows_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, con
   {
     APC_PROF(ctx, "k_sort_keys", s);
     const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
-    k_sort_keys<<<blocks, 256, 0, s>>>(pts, n_max, n_dev, ctx->sort_a, ctx->sort_hist);
+    k_sort_keys<false><<<blocks, 256, 0, s>>>(pts, n_max, n_dev, ctx->sort_a, ctx->sort_hist, 0.0f, ctx->ctrl);
     APC_LAUNCH_CHECK(ctx, "k_sort_keys");
   }
   uint4 *a = ctx->sort_a, *b = ctx->sort_b;
@@ -281,6 +299,115 @@ int apc_unique_rows_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, con
   k_unique_heads<<<n_tiles, APC_TILE_THREADS, 0, s>>>(a, n_max, n_dev, out_first_idx, out_inverse, out_count_dev,
                                                       ctx->scan_state[scan_slot], ctx->ctrl, n_tiles);
   APC_LAUNCH_CHECK(ctx, "k_unique_heads");
+  return APC_OK;
+}
+
+// ---- sort-based voxel grid: the alternative north_star (3) names, kept for the A/B against the hash ----
+// One thread per sorted record; the head of a run (key differs from its predecessor) walks the run -
+// stable sort, so in input order - and accumulates the same fixed-point sums as voxel.cu (order
+// independent, so the centroids are bit-identical to the hash path's), then writes the voxel at its
+// rank among the heads.  Output order: ascending (ix, iy, iz) - the other canonical order SURVEY.md
+// section 8(c) allows - not first occurrence.
+__device__ __forceinline__ unsigned long long seg_fixed(float v, double scale) {
+  return (unsigned long long)__double2ll_rn((double)v * scale);
+}
+__global__ void __launch_bounds__(APC_TILE_THREADS)
+k_voxel_segreduce(const uint4* __restrict__ sorted, const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev,
+                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count, uint64_t* scan_state,
+                  const ApcCtrl* ctrl, uint32_t n_tiles) {
+  __shared__ uint32_t sm_scan[34];
+  const uint32_t n = apc_count(n_dev, n_max);
+  const uint32_t epoch = ctrl->epoch;
+  const uint32_t tile = blockIdx.x;
+  bool head[APC_TILE_ITEMS];
+  float4 cen[APC_TILE_ITEMS];
+  uint32_t cnt[APC_TILE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j) {
+    const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
+    head[j] = false;
+    cnt[j] = 0u;
+    if (i < n) {
+      const uint4 c = sorted[i];
+      if (i == 0) head[j] = true;
+      else {
+        const uint4 p = sorted[i - 1];
+        head[j] = c.x != p.x || c.y != p.y || c.z != p.z;
+      }
+      if (head[j]) {
+        unsigned long long sx = 0, sy = 0, sz = 0, sw = 0;
+        uint32_t e = i;
+        uint4 r = c;
+        do {
+          const float4 q = pts[r.w];
+          sx += seg_fixed(q.x, 16777216.0); sy += seg_fixed(q.y, 16777216.0); sz += seg_fixed(q.z, 16777216.0);
+          sw += seg_fixed(q.w, 1048576.0);
+          ++cnt[j];
+          if (++e >= n) break;
+          r = sorted[e];
+        } while (r.x == c.x && r.y == c.y && r.z == c.z);
+        const double dc = (double)cnt[j];
+        cen[j] = make_float4(
+            __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sx), dc), 1.0 / 16777216.0)),
+            __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sy), dc), 1.0 / 16777216.0)),
+            __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sz), dc), 1.0 / 16777216.0)),
+            __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn((long long)sw), dc), 1.0 / 1048576.0)));
+      }
+    }
+  }
+  uint32_t rank[APC_TILE_ITEMS];
+  const uint32_t base = tile_compact_offsets(head, rank, sm_scan, scan_state, tile, epoch, out_count, n_tiles);
+#pragma unroll
+  for (int j = 0; j < APC_TILE_ITEMS; ++j)
+    if (head[j]) {
+      out[base + rank[j]] = cen[j];
+      if (out_counts) out_counts[base + rank[j]] = cnt[j];
+    }
+}
+
+extern "C" int apc_voxel_downsample_sorted(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                                           float voxel_size, float* out_xyzi, uint32_t* out_voxel_counts,
+                                           uint32_t* out_count_dev, void* stream) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  APC_REQUIRE(ctx, out_count_dev, "out_count_dev is NULL");
+  APC_REQUIRE(ctx, voxel_size > 0.0f, "voxel_size must be > 0");
+  APC_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = apc_sort_prepare(ctx);
+  if (rc) return rc;
+  rc = apc_begin(ctx, s);
+  if (rc) return rc;
+  if (n_max == 0) {
+    APC_CUDA(ctx, cudaMemsetAsync(out_count_dev, 0, sizeof(uint32_t), s));
+    return APC_OK;
+  }
+  APC_REQUIRE(ctx, xyzi && out_xyzi, "NULL pointer");
+  APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  const float4* pts = reinterpret_cast<const float4*>(xyzi);
+  APC_CUDA(ctx, cudaMemsetAsync(ctx->sort_hist, 0, SORT_PASSES * 256 * sizeof(uint32_t), s));
+  {
+    APC_PROF(ctx, "k_sort_keys", s);
+    const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
+    k_sort_keys<true><<<blocks, 256, 0, s>>>(pts, n_max, n_dev, ctx->sort_a, ctx->sort_hist, voxel_size, ctx->ctrl);
+    APC_LAUNCH_CHECK(ctx, "k_sort_keys");
+  }
+  uint4 *a = ctx->sort_a, *b = ctx->sort_b;
+  const uint32_t sort_tiles = apc_div_up(n_max, SORT_TILE);
+  for (uint32_t pass = 0; pass < SORT_PASSES; ++pass) {
+    if ((pass & 3u) == 3u) continue;       // voxel indices are 21 bits: the top byte of every component is zero
+    APC_PROF(ctx, "k_sort_pass", s);
+    k_sort_pass<<<sort_tiles, SORT_THREADS, 0, s>>>(a, b, n_max, n_dev, ctx->sort_hist, ctx->sort_status, pass, ctx->ctrl);
+    APC_LAUNCH_CHECK(ctx, "k_sort_pass");
+    uint4* tmp = a;
+    a = b;
+    b = tmp;
+  }
+  const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
+  APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
+  APC_PROF(ctx, "k_voxel_segreduce", s);
+  k_voxel_segreduce<<<n_tiles, APC_TILE_THREADS, 0, s>>>(a, pts, n_max, n_dev, reinterpret_cast<float4*>(out_xyzi),
+                                                         out_voxel_counts, out_count_dev, ctx->scan_state[1], ctx->ctrl, n_tiles);
+  APC_LAUNCH_CHECK(ctx, "k_voxel_segreduce");
   return APC_OK;
 }
 

@@ -254,6 +254,17 @@ class Context:
                                           _ptr(p2v), _ptr(vc), _ptr(cnt), _stream()))
         return out, p2v, vc, cnt
 
+    def voxel_downsample_sorted(self, xyzi, voxel_size, want_counts=False, n_dev=None):
+        """The sort-based voxel grid (``apc_voxel_downsample_sorted``): same voxels / counts / centroids as
+        :meth:`voxel_downsample`, rows in ascending (ix, iy, iz) order."""
+        n = xyzi.shape[0]
+        out = self._empty((max(n, 1), 4), torch.float32)
+        vc = self._empty((max(n, 1),), torch.int32) if want_counts else None
+        cnt = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._ok(lib.apc_voxel_downsample_sorted(self.h, _ptr(xyzi), n, _ptr(n_dev), float(voxel_size), _ptr(out),
+                                                 _ptr(vc), _ptr(cnt), _stream()))
+        return out, vc, cnt
+
     def voxel_mean_attr(self, attr_f32, p2v, n_voxels_dev, n_vox_max):
         out = self._empty((max(n_vox_max, 1),), torch.float32)
         self._ok(lib.apc_voxel_mean_attr(self.h, _ptr(attr_f32), _ptr(p2v), attr_f32.shape[0], None,

@@ -177,6 +177,7 @@ class TensorMap(dict):
 # ---- contexts ----------------------------------------------------------------------------------------
 
 _CONTEXTS: dict = {}
+MAX_CONTEXT_POINTS = 1 << 22         # apc_ctx_create's limit
 
 
 def get_context(n_points: int, device_index: int | None = None) -> engine.Context:
@@ -184,13 +185,15 @@ def get_context(n_points: int, device_index: int | None = None) -> engine.Contex
     idx = torch.cuda.current_device() if device_index is None else device_index
     ctx = _CONTEXTS.get(idx)
     need = max(int(n_points), 1)
+    if need > MAX_CONTEXT_POINTS:          # refuse before touching the shared context (parameter caps)
+        raise ValueError(f"clouds of more than {MAX_CONTEXT_POINTS} points are not supported ({need} requested)")
     if ctx is None or ctx.max_points < need:
         cap = 1 << 16
         while cap < need:
             cap <<= 1
         if ctx is not None:
             ctx.close()
-        ctx = engine.Context(max_points=min(cap, 1 << 22), device=idx)
+        ctx = engine.Context(max_points=min(cap, MAX_CONTEXT_POINTS), device=idx)
         _CONTEXTS[idx] = ctx
     return ctx
 

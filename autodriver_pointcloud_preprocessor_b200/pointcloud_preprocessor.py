@@ -51,7 +51,7 @@ from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, Duration, Ext
                           LookupException, Node, Parameter, ParameterDescriptor, ParameterType, PointCloud2,
                           PointField, QoSHistoryPolicy, QoSProfile, QoSReliabilityPolicy, SetParametersResult,
                           Time, TransformListener, point_cloud2, rclpy, tf2_ros)
-from .utils import (raw_column, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
+from .utils import (raw_column, packed_message_bytes, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
                     convert_pointcloud_to_numpy, crop_pointcloud, dict_to_open3d_tensor_pointcloud,
                     extract_rgb_from_pointcloud, get_current_time, get_fields_from_dicts, get_pointcloud_metadata,
                     get_time_difference, numpy_struct_to_pointcloud2, pointcloud_to_dict, remove_duplicates,
@@ -311,8 +311,7 @@ class PointcloudPreprocessorNode(Node):
             self._fused_xyzi = None
             n = ros_cloud.width * ros_cloud.height
             # one upload of the message bytes per scan; both paths read this device buffer
-            self._raw_dev = (torch.frombuffer(bytearray(ros_cloud.data), dtype=torch.uint8) if n
-                             else torch.zeros(16, dtype=torch.uint8)).cuda()
+            self._raw_dev = packed_message_bytes(ros_cloud).cuda()      # row padding (row_step) removed on the way up
             names = tuple(field_names) if field_names else tuple(f.name for f in ros_cloud.fields)
             if not (self.pointcloud_metadata or {}).get('has_intensity', False):
                 self.pointcloud_metadata = dict(self.pointcloud_metadata or {}, **get_pointcloud_metadata(names))
@@ -388,6 +387,7 @@ class PointcloudPreprocessorNode(Node):
         return self._preprocess_staged()
 
     def _preprocess_fused(self):
+        fused_start_time = get_current_time(monotonic=True)
         msg = self._raw_msg
         n = msg.width * msg.height
         ctx = geometry.get_context(n)
@@ -474,6 +474,17 @@ class PointcloudPreprocessorNode(Node):
         self._fused_xyzi = (out[:n_out], cloud)       # prepare_pointcloud repacks straight from this
         self.last_counts = c
         self.last_plane = plane.cpu().numpy()
+        # the stages ran as ONE launch chain: the reference's per-stage keys (pp.py:463-543) exist for every
+        # enabled stage, the time of the whole chain is booked under 'fused_pipeline'
+        fused_time = get_time_difference(fused_start_time, get_current_time(monotonic=True))
+        for key, on in (('remove_duplicate_points', self.remove_duplicates), ('remove_nan_points', self.remove_nans or self.remove_infs),
+                        ('transform', bool(self._transforms())), ('crop', self.crop_to_roi),
+                        ('voxel_downsampling', self.voxel_size > 0.0),
+                        ('remove_statistical_outliers', self.remove_statistical_outliers),
+                        ('normal_estimation', self.estimate_normals), ('ground_segmentation', self.remove_ground)):
+            if on:
+                self.processing_times[key] = 0.0
+        self.processing_times['fused_pipeline'] = fused_time
         return self.o3d_pointcloud
 
     def _normals_and_ground(self):

@@ -122,6 +122,23 @@ def numpy_struct_to_pointcloud2(field_names: list,
     return fields, offset
 
 
+def packed_message_bytes(ros_cloud):
+    """The message's point records as one tightly packed host uint8 tensor ``[n * point_step]``.
+    ``read_points`` honours ``row_step`` (organised clouds may pad their rows); the kernels expect
+    ``width * height`` consecutive records, so padded rows are compacted here, on the way to the GPU."""
+    n = ros_cloud.width * ros_cloud.height
+    if n == 0:
+        return torch.zeros(16, dtype=torch.uint8)
+    raw = torch.frombuffer(bytearray(ros_cloud.data), dtype=torch.uint8)
+    tight = ros_cloud.width * ros_cloud.point_step
+    row_step = int(getattr(ros_cloud, "row_step", 0) or tight)
+    if row_step != tight:
+        if row_step < tight or raw.numel() < row_step * ros_cloud.height:
+            raise ValueError(f"PointCloud2 row_step {row_step} is inconsistent with width*point_step {tight}")
+        raw = raw[:row_step * ros_cloud.height].view(ros_cloud.height, row_step)[:, :tight].contiguous().view(-1)
+    return raw
+
+
 def raw_column(rows, field):
     """One field of every record of a device byte buffer viewed as ``[n, point_step]``: a contiguous
     device tensor of the field's own dtype (the per-field slice ``read_points`` returns)."""
@@ -162,8 +179,7 @@ def pointcloud_to_dict(ros_cloud, field_names=None, skip_nans=True, organize_clo
     if _data_dev is not None:              # the node uploads the message once and shares the buffer
         data = _data_dev
     else:
-        raw = torch.frombuffer(bytearray(ros_cloud.data), dtype=torch.uint8) if n else torch.zeros(16, dtype=torch.uint8)
-        data = raw.cuda()
+        data = packed_message_bytes(ros_cloud).cuda()
     ctx = geometry.get_context(n)
     desc = engine.make_cloud_desc(ros_cloud.fields, ros_cloud.point_step, n, data, field_names=field_names)
     cfg = engine.make_filter_cfg(skip_nans=bool(skip_nans and not ros_cloud.is_dense))

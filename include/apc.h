@@ -204,6 +204,16 @@ int apc_voxel_downsample(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const 
                          float voxel_size, float* out_xyzi, int32_t* out_p2v,
                          uint32_t* out_voxel_counts, uint32_t* out_count_dev, void* stream);
 
+/* The same voxel grid by SORTING instead of hashing - the alternative BASELINE.json north_star (3) names
+ * ("a hand-written onesweep radix sort, followed by a segmented centroid reduce"): biased 21-bit voxel
+ * indices -> stable LSD radix sort of {ix, iy, iz, index} (9 byte passes, identity passes collapse) ->
+ * segmented fixed-point reduce.  Same voxels, counts and bit-identical centroids as
+ * apc_voxel_downsample, but in ASCENDING (ix, iy, iz) order instead of first-occurrence order.  Kept
+ * for the hash-vs-sort comparison (profiles/voxel_ab.py); the pipeline uses the hash. */
+int apc_voxel_downsample_sorted(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uint32_t* n_dev,
+                                float voxel_size, float* out_xyzi, uint32_t* out_voxel_counts,
+                                uint32_t* out_count_dev, void* stream);
+
 /* Per-attribute voxel mean "in float32 then cast back" (Open3D index_add per attribute,
  * SURVEY.md B7) for a float32 attribute, using p2v / counts from apc_voxel_downsample. */
 int apc_voxel_mean_attr(apc_ctx* ctx, const float* attr, const int32_t* p2v, uint32_t n_max,

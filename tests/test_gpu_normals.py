@@ -27,12 +27,23 @@ def to_xyzi(p):
 
 
 def check_normals(got, cov, ref, atol=1e-5):
-    """got / ref float32[N,3]; cov float64[N,3,3] (oracle)."""
+    """got / ref float32[N,3]; cov float64[N,3,3] (oracle).
+
+    The bound on the worst deviation: an eigenvector moves by at most |dC| / gap when the matrix moves
+    by dC; the GPU's covariance is within 1e-9 of the oracle's (relative to its largest entry, asserted in
+    test_normals_parity), so EVERY normal must satisfy
+        max_k |got_k - ref_k|  <=  1e-5 + 1e-7 * lambda_max / (lambda_1 - lambda_0)
+    i.e. 1e-5 wherever the two smallest eigenvalues are separated by 1 % of the largest, degrading
+    gracefully towards degenerate neighbourhoods (collinear points), where the direction itself is
+    ill-defined and only the eigen-residual bound below is meaningful."""
     w = np.linalg.eigvalsh(cov)                                   # ascending
     scale = np.maximum(w[:, 2], 1e-300)
-    separated = (w[:, 1] - w[:, 0]) / scale > 1e-6
+    gap = np.maximum(w[:, 1] - w[:, 0], 1e-300)
+    separated = gap / scale > 1e-2
     assert separated.sum() > 50
-    assert np.allclose(got[separated], ref[separated], rtol=0, atol=atol)
+    dev = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max(axis=1)
+    assert np.all(dev[separated] <= atol + 1e-5), float(dev[separated].max())
+    assert np.all(dev <= atol + 1e-7 * scale / gap), float((dev - 1e-7 * scale / gap).max())
     # everywhere: a unit vector (or exactly one of the axis fallbacks) whose Rayleigh quotient is the smallest eigenvalue
     n64 = got.astype(np.float64)
     assert np.allclose(np.linalg.norm(n64, axis=1), 1.0, atol=1e-5)

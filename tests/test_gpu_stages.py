@@ -516,3 +516,32 @@ def test_pipeline_random_stage_combinations(env, seed):
         assert same_f32(got[:, 3], ref["intensity"]), (mode, what)
         if stages.get("ground") and ref["ground_inliers"].size >= 3:
             assert np.allclose(plane.cpu().numpy()[:4], ref["plane"], rtol=0, atol=1e-5), (mode, what)
+
+
+@pytest.mark.parametrize("voxel_size", [0.1, 0.37])
+def test_voxel_sorted_equals_hash(env, voxel_size):
+    """The sort-based voxel grid (onesweep radix sort + segmented reduce, the alternative north_star (3)
+    names) produces the same voxels as the hash: identical counts and bit-identical centroids, in
+    ascending (ix, iy, iz) order instead of first-occurrence order."""
+    ctx = env["ctx"]
+    xyzi, pts = filtered_cloud(env)
+    out_h, p2v, vc_h, cnt_h = ctx.voxel_downsample(xyzi, voxel_size, want_p2v=True, want_counts=True)
+    out_s, vc_s, cnt_s = ctx.voxel_downsample_sorted(xyzi, voxel_size, want_counts=True)
+    ctx.check()
+    v = int(cnt_h.item())
+    assert v == int(cnt_s.item()) and v > 100
+    h = np.concatenate([out_h[:v].cpu().numpy().view(np.uint32), vc_h[:v].cpu().numpy().view(np.uint32)[:, None]], 1)
+    s = np.concatenate([out_s[:v].cpu().numpy().view(np.uint32), vc_s[:v].cpu().numpy().view(np.uint32)[:, None]], 1)
+    # same multiset of (centroid bits, count) rows
+    assert np.array_equal(h[np.lexsort(h.T[::-1])], s[np.lexsort(s.T[::-1])])
+    # the sorted path's order: strictly ascending voxel index, x-major.  The index of a voxel is that of
+    # its member points (floor(x / voxel_size) in float32, the kernels' arithmetic), looked up through
+    # the hash path's point -> voxel map; rows are matched by their centroid bits.
+    q = np.floor(pts[:, :3] / np.float32(voxel_size)).astype(np.int64)
+    key_of_point = ((q[:, 0] + (1 << 20)) << 42) | ((q[:, 1] + (1 << 20)) << 21) | (q[:, 2] + (1 << 20))
+    key_of_row = np.zeros(v, dtype=np.int64)
+    key_of_row[p2v.cpu().numpy()[:pts.shape[0]]] = key_of_point
+    by_bits = {tuple(r): k for r, k in zip(map(tuple, h), key_of_row)}
+    assert len(by_bits) == v                                     # centroid + count identify a voxel here
+    keys_sorted = np.array([by_bits[tuple(r)] for r in s])
+    assert np.all(np.diff(keys_sorted) > 0)
