@@ -15,6 +15,7 @@
 // until the k-th distance is covered by the 27-cell block, and the rare points that never
 // are (fewer than k points in range of the coarsest level) fall to an exact brute-force
 // kernel.  The table is cleaned by the points that own rank 0 of their cell, not by memset.
+#include <cstdlib>
 #include "apc_scan.cuh"
 #include "apc_grid.cuh"
 APC_TRACE_EXPORT(neighbors)
@@ -194,6 +195,45 @@ __device__ __forceinline__ uint32_t grid_sorted_count(const GridDev& g, const Ap
 }
 
 // ---- radius query -----------------------------------------------------------------------------
+// Neighbours of q within r2 among the first `n_cells` cells of the centre-first order (1 = own cell
+// only, 27 = the whole block), stopping at nb_points unless the exact count is wanted.
+__device__ __forceinline__ uint32_t radius_count(const GridDev& g, float c, float4 q, float r2, uint32_t nb_points,
+                                                 int need_counts, int n_cells) {
+  int32_t ix, iy, iz;
+  grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+  uint32_t cnt = 0;
+  // own cell first, then faces, edges, corners: when only the keep/drop decision is wanted
+  // most points reach nb_points inside their own cell and stop there.  The first probe of the
+  // NEXT cell is in flight while the current cell's points are scanned.
+  uint64_t key = grid_key(0, ix, iy, iz);
+  uint32_t home = grid_home(g, key);
+  uint4 first = grid_load(g, home);
+  for (int c27 = 0; c27 < n_cells && (need_counts || cnt < nb_points); ++c27) {
+    const uint64_t key_now = key;
+    const uint32_t home_now = home;
+    const uint4 first_now = first;
+    if (c27 + 1 < n_cells) {
+      const int code = c_cell_order[c27 + 1];
+      key = grid_key(0, ix + code % 3 - 1, iy + (code / 3) % 3 - 1, iz + code / 9 - 1);
+      home = grid_home(g, key);
+      first = grid_load(g, home);
+    }
+    uint32_t b, f;
+    if (!grid_resolve(g, key_now, home_now, first_now, b, f)) continue;
+    const uint32_t e = b + f;
+    // four points per round: their loads are independent, the exit test runs once per round
+    for (uint32_t t = b; t < e && (need_counts || cnt < nb_points); t += 4) {
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = g.sorted[min(t + u, e - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        cnt += (t + u < e && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
+    }
+  }
+  return cnt;
+}
+
 __global__ void __launch_bounds__(128)
 k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
                uint8_t* __restrict__ mask, uint32_t* __restrict__ counts, const ApcCtrl* __restrict__ ctrl) {
@@ -203,42 +243,77 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
-    int32_t ix, iy, iz;
-    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
-    uint32_t cnt = 0;
-    // own cell first, then faces, edges, corners: when only the keep/drop decision is wanted
-    // most points reach nb_points inside their own cell and stop there.  The first probe of the
-    // NEXT cell is in flight while the current cell's points are scanned.
-    uint64_t key = grid_key(0, ix, iy, iz);
-    uint32_t home = grid_home(g, key);
-    uint4 first = grid_load(g, home);
-    for (int c27 = 0; c27 < 27 && (need_counts || cnt < nb_points); ++c27) {
-      const uint64_t key_now = key;
-      const uint32_t home_now = home;
-      const uint4 first_now = first;
-      if (c27 + 1 < 27) {
-        const int code = c_cell_order[c27 + 1];
-        key = grid_key(0, ix + code % 3 - 1, iy + (code / 3) % 3 - 1, iz + code / 9 - 1);
-        home = grid_home(g, key);
-        first = grid_load(g, home);
-      }
-      uint32_t b, f;
-      if (!grid_resolve(g, key_now, home_now, first_now, b, f)) continue;
-      const uint32_t e = b + f;
-      // four points per round: their loads are independent, the exit test runs once per round
-      for (uint32_t t = b; t < e && (need_counts || cnt < nb_points); t += 4) {
-        float4 p[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) p[u] = g.sorted[min(t + u, e - 1)];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          cnt += (t + u < e && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
-      }
-    }
+    const uint32_t cnt = radius_count(g, c, q, r2, nb_points, need_counts, 27);
     mask[orig] = cnt >= nb_points ? 1 : 0;
     if (counts) counts[orig] = cnt;
   }
   APC_STAMP(0, 1);
+}
+
+// The keep / drop decision in two launches (the exact counts are not wanted):
+//   fast  every point against its OWN cell only - one probe, one or two rounds of loads, every thread
+//         done within the same few microseconds; the few that did not reach nb_points there are
+//         appended (warp-aggregated) to a pending list;
+//   slow  the pending points against the whole 27-cell block.
+// One launch doing both keeps ALL threads' registers resident until the slowest walker of each CTA is
+// through its 27 dependent probes (22 us at C2 for work most threads finish in 4): the split hands the
+// register file back to the other lanes' kernels.
+#define CTR_RADIUS_PENDING 23
+__global__ void __launch_bounds__(128)
+k_radius_fast(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, uint8_t* __restrict__ mask,
+              uint32_t* __restrict__ pending, ApcCtrl* ctrl) {
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
+  const float c = grid_cell_size(g, 0);
+  const uint32_t lane = lane_id();
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t j = base + threadIdx.x;
+    bool open = false;
+    if (j < n) {
+      const float4 q = g.sorted[j];
+      const uint32_t cnt = radius_count(g, c, q, r2, nb_points, 0, 1);
+      open = cnt < nb_points;
+      if (!open) mask[__float_as_uint(q.w)] = 1;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, open);
+    if (bal) {
+      uint32_t at = 0;
+      if (lane == 0) at = atomicAdd(&ctrl->counters[CTR_RADIUS_PENDING], (uint32_t)__popc(bal));
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (open) pending[at + __popc(bal & ((1u << lane) - 1u))] = j;
+    }
+  }
+}
+__global__ void __launch_bounds__(128)
+k_radius_slow(GridDev g, float r2, uint32_t nb_points, uint8_t* __restrict__ mask, const uint32_t* __restrict__ pending,
+              const ApcCtrl* __restrict__ ctrl) {
+  const uint32_t n = ctrl->counters[CTR_RADIUS_PENDING];
+  const float c = grid_cell_size(g, 0);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const float4 q = g.sorted[pending[k]];
+    const uint32_t cnt = radius_count(g, c, q, r2, nb_points, 0, 27);
+    mask[__float_as_uint(q.w)] = cnt >= nb_points ? 1 : 0;
+  }
+}
+
+// decision-only radius query: split (default) or the single launch (APC_RADIUS_SPLIT=0)
+static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const uint32_t* n_dev, float r2, uint32_t nb_points,
+                         uint8_t* mask, cudaStream_t s) {
+  static const bool split = []() { const char* e = getenv("APC_RADIUS_SPLIT"); return !e || atoi(e) != 0; }();
+  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  if (!split) {
+    APC_PROF(ctx, "k_radius_query", s);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    APC_LAUNCH_CHECK(ctx, "k_radius_query");
+    return APC_OK;
+  }
+  {
+    APC_PROF(ctx, "k_radius_fast", s);
+    k_radius_fast<<<bq, 128, 0, s>>>(n_max, n_dev, g, r2, nb_points, mask, ctx->nb_count, ctx->ctrl);
+  }
+  APC_PROF(ctx, "k_radius_slow", s);
+  k_radius_slow<<<min(bq, (uint32_t)APC_SM_COUNT * 4), 128, 0, s>>>(g, r2, nb_points, mask, ctx->nb_count, ctx->ctrl);
+  APC_LAUNCH_CHECK(ctx, "k_radius_fast/slow");
+  return APC_OK;
 }
 
 // ---- KNN query ---------------------------------------------------------------------------------
@@ -703,10 +778,13 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
   if (rc) return rc;
-  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
-  {
+  if (out_counts) {
+    const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
     APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, out_counts != nullptr, out_mask, out_counts, ctx->ctrl);
+    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
+  } else {
+    rc = radius_decide(ctx, g.d, n_max, n_dev, r2, (uint32_t)nb_points, out_mask, s);
+    if (rc) return rc;
   }
   const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
   APC_PROF(ctx, "k_grid_clean", s);
@@ -789,11 +867,8 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s, points_inserted != 0);
   if (rc) return rc;
-  const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
-  {
-    APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r32 * r32, (uint32_t)nb_points, 0, mask_scratch, nullptr, ctx->ctrl);
-  }
+  rc = radius_decide(ctx, g.d, n_max, n_dev, r32 * r32, (uint32_t)nb_points, mask_scratch, s);
+  if (rc) return rc;
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
   APC_PROF(ctx, "k_radius_select", s);

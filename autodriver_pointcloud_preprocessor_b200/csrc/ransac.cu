@@ -14,6 +14,7 @@
 //   - the last CTA to retire applies Open3D's sequential selection / early-stop rule;
 //   - final pass: inlier mask against the winning hypothesis + moment sums for the
 //     least-squares refit, reduced in a fixed order.
+#include <cmath>
 #include <cstdlib>
 #include "apc_scan.cuh"
 APC_TRACE_EXPORT(ransac)
@@ -123,7 +124,7 @@ __device__ __forceinline__ double plane_dist(const double* pl, double x, double 
 #define CTR_RS_SCORE_TICKET 21  // ctrl->counters slot: retired CTAs of k_rs_score
 __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes, const unsigned long long* scores_in,
                                            uint32_t n_rows, uint32_t row_stride, uint32_t P, uint32_t ransac_n,
-                                           uint32_t iters, double prob, double* __restrict__ plane8,
+                                           uint32_t iters, double log1mp, double* __restrict__ plane8,
                                            uint32_t* __restrict__ info, unsigned long long* __restrict__ scores_copy);
 
 // Scoring + selection in one launch (the hypotheses come from k_rs_hypotheses).
@@ -222,10 +223,10 @@ k_rs_hypotheses(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* 
 }
 
 template <int CH>
-__global__ void __launch_bounds__(APC_TILE_THREADS, 1)
+__global__ void __launch_bounds__(APC_TILE_THREADS, CH <= 10 ? 3 : 1)
 k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, uint32_t ransac_n, uint32_t iters,
            const double* __restrict__ planes, double thr,
-           unsigned long long* scores, double prob, double* __restrict__ plane8, uint32_t* __restrict__ info,
+           unsigned long long* scores, double log1mp, double* __restrict__ plane8, uint32_t* __restrict__ info,
            unsigned long long* __restrict__ scores_copy, ApcCtrl* ctrl) {
   static_assert(CH % 2 == 0, "hypotheses are scored in pairs");
   __shared__ double s_pl[CH][4];
@@ -398,7 +399,7 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   RS_STAMP(4);
   APC_STAMP(0, 1);
   if (!s_last) return;
-  rs_select_cta(planes, scores, gridDim.x, gridDim.y * CH, P, ransac_n, iters, prob, plane8, info, scores_copy);
+  rs_select_cta(planes, scores, gridDim.x, gridDim.y * CH, P, ransac_n, iters, log1mp, plane8, info, scores_copy);
   RS_STAMP(5);
   APC_STAMP(0, 2);
 }
@@ -413,7 +414,7 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
 // info = {best iteration | 0xffffffff, n_inliers (filled later), 0, 0}; plane8[4..7] = winner.
 __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes_in, const unsigned long long* scores_in,
                                            uint32_t n_rows, uint32_t row_stride, uint32_t P, uint32_t ransac_n,
-                                           uint32_t iters, double prob, double* __restrict__ plane8,
+                                           uint32_t iters, double log1mp, double* __restrict__ plane8,
                                            uint32_t* __restrict__ info, unsigned long long* __restrict__ scores_copy) {
   const double* planes = planes_in;                 // written by k_rs_hypotheses, the previous launch
   __shared__ unsigned long long s_wmax[APC_TILE_THREADS / 32];
@@ -425,7 +426,6 @@ __device__ __noinline__ void rs_select_cta(const double* __restrict__ planes_in,
   __shared__ double sb_break;
   __shared__ bool sb_stop;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const double log1mp = prob < 1.0 ? log(1.0 - prob) : -__longlong_as_double(0x7ff0000000000000ll);
   if (tid == 0) { s_carry = 0; sb_it = 0xffffffffu; sb_break = (double)iters; sb_stop = false; }
   __syncthreads();
   __shared__ ulonglong2 s_half[APC_TILE_THREADS / 2];
@@ -660,19 +660,26 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
-  // hypotheses per CTA: 16 or 20, whichever pads num_iterations less (100 = 5 x 20)
-  const uint32_t pad16 = apc_div_up(iters, 16) * 16, pad20 = apc_div_up(iters, 20) * 20;
-  const uint32_t ch = pad20 < pad16 ? 20u : 16u;
+  // hypotheses per CTA (CH) and CTAs per SM.  CH = 20 / 16 with ONE CTA per SM (142 / 128 registers), or
+  // CH = 10 / 8 with TWO (<= 96 registers): the same arithmetic per SM, but a CTA's fixed phases (plane
+  // staging, flush, ticket) overlap the other CTA's scoring and every CTA scores half as many planes per
+  // tile.  APC_RS_CH picks the chunk (default 10: profiles/r2*_rs_trace*.txt).
+  static const uint32_t ch_env = []() { const char* e = getenv("APC_RS_CH"); return e ? (uint32_t)atoi(e) : 10u; }();
+  uint32_t ch;
+  if (ch_env == 20 || ch_env == 16) {
+    const uint32_t pad16 = apc_div_up(iters, 16) * 16, pad20 = apc_div_up(iters, 20) * 20;
+    ch = pad20 < pad16 ? 20u : 16u;               // whichever pads num_iterations less (100 = 5 x 20)
+  } else {
+    const uint32_t pad8 = apc_div_up(iters, 8) * 8, pad10 = apc_div_up(iters, 10) * 10;
+    ch = pad10 <= pad8 ? 10u : 8u;
+  }
   const uint32_t n_chunks = apc_div_up(iters, ch);
-  // ONE resident CTA per SM in total, each striding over the same number of point tiles.  The
-  // kernel's own duration is the same with two (27.6 vs 27.9 us: prologue, flush and selection do
-  // not shrink), but at 124 registers two CTAs own an SM's whole register file and shut the other
-  // lanes' kernels out: one per SM measured 74.9 instead of 77.2 us/scan with 8 lanes.
-  // APC_RS_HALF_CTAS_PER_SM (in half CTAs per SM) overrides for experiments.
-  static const uint32_t ctas_x2 = []() { const char* e = getenv("APC_RS_HALF_CTAS_PER_SM"); return e ? min(max((uint32_t)atoi(e), 1u), 4u) : 2u; }();   // the tally rows are sized for <= 2 CTAs per SM
-  const uint32_t gx0 = min(n_tiles, max(1u, (uint32_t)(APC_SM_COUNT * ctas_x2 / 2) / n_chunks));
+  const uint32_t ctas_per_sm = ch <= 10 ? 2u : 1u;
+  // every CTA strides over the same number of point tiles; the per-CTA tally rows are sized for <= 2 CTAs per SM
+  const uint32_t gx0 = min(n_tiles, max(1u, (uint32_t)(APC_SM_COUNT * ctas_per_sm) / n_chunks));
   const uint32_t gx = apc_div_up(n_tiles, apc_div_up(n_tiles, gx0));
   const dim3 grid(gx, n_chunks);
+  const double log1mp = prob < 1.0 ? log(1.0 - prob) : -INFINITY;
   {
     APC_PROF(ctx, "k_rs_hypotheses", s);
     k_rs_hypotheses<<<apc_div_up(iters, RS_HYP_THREADS), RS_HYP_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table,
@@ -680,12 +687,14 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   }
   {
     APC_PROF(ctx, "k_rs_score", s);
-    if (ch == 20)
-      k_rs_score<20><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr,
-                                                       ctx->rs_scores, prob, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl);
-    else
-      k_rs_score<16><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr,
-                                                       ctx->rs_scores, prob, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl);
+#define RS_LAUNCH(CHV)                                                                                              \
+  k_rs_score<CHV><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr, ctx->rs_scores, \
+                                                    log1mp, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl)
+    if (ch == 20) RS_LAUNCH(20);
+    else if (ch == 16) RS_LAUNCH(16);
+    else if (ch == 10) RS_LAUNCH(10);
+    else RS_LAUNCH(8);
+#undef RS_LAUNCH
   }
   APC_PROF(ctx, "k_rs_final", s);
   k_rs_final<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials,
