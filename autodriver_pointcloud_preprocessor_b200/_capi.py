@@ -95,7 +95,7 @@ def _load():
         "apc_split_xyzi": [vp, vp, u32, vp, vp, vp, vp],
         "apc_voxel_downsample": [vp, vp, u32, vp, C.c_float, vp, vp, vp, vp, vp],
         "apc_voxel_downsample_sorted": [vp, vp, u32, vp, C.c_float, vp, vp, vp, vp],
-        "apc_voxel_mean_attr": [vp, vp, vp, u32, vp, vp, vp, vp],
+        "apc_voxel_mean_attr": [vp, vp, vp, u32, vp, vp, i32, vp, vp],
         "apc_radius_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp],
         "apc_statistical_outliers": [vp, vp, u32, vp, i32, f64, vp, vp, vp, vp],
         "apc_estimate_normals": [vp, vp, u32, vp, i32, f64, vp, vp, vp, vp],

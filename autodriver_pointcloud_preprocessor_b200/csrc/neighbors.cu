@@ -255,9 +255,10 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
 //         done within the same few microseconds; the few that did not reach nb_points there are
 //         appended (warp-aggregated) to a pending list;
 //   slow  the pending points against the whole 27-cell block.
-// One launch doing both keeps ALL threads' registers resident until the slowest walker of each CTA is
-// through its 27 dependent probes (22 us at C2 for work most threads finish in 4): the split hands the
-// register file back to the other lanes' kernels.
+// Idea: one launch doing both keeps ALL threads' registers resident until the slowest walker of each CTA
+// is through its 27 dependent probes.  Measured (APC_RADIUS_SPLIT=1, profiles/r2g_knobs.json): the own-cell
+// pass takes 10.6 us, but the pending pass still takes 23 us (its walkers are the whole cost) and saturated
+// throughput does not move (70.5 vs 70.8 us/scan), for one more launch of latency: OFF by default.
 #define CTR_RADIUS_PENDING 23
 __global__ void __launch_bounds__(128)
 k_radius_fast(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, uint8_t* __restrict__ mask,
@@ -295,10 +296,10 @@ k_radius_slow(GridDev g, float r2, uint32_t nb_points, uint8_t* __restrict__ mas
   }
 }
 
-// decision-only radius query: split (default) or the single launch (APC_RADIUS_SPLIT=0)
+// decision-only radius query: the single launch (default) or the split (APC_RADIUS_SPLIT=1)
 static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const uint32_t* n_dev, float r2, uint32_t nb_points,
                          uint8_t* mask, cudaStream_t s) {
-  static const bool split = []() { const char* e = getenv("APC_RADIUS_SPLIT"); return !e || atoi(e) != 0; }();
+  static const bool split = []() { const char* e = getenv("APC_RADIUS_SPLIT"); return e && atoi(e) != 0; }();
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   if (!split) {
     APC_PROF(ctx, "k_radius_query", s);

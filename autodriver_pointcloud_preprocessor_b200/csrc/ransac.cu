@@ -660,11 +660,12 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
-  // hypotheses per CTA (CH) and CTAs per SM.  CH = 20 / 16 with ONE CTA per SM (142 / 128 registers), or
-  // CH = 10 / 8 with TWO (<= 96 registers): the same arithmetic per SM, but a CTA's fixed phases (plane
-  // staging, flush, ticket) overlap the other CTA's scoring and every CTA scores half as many planes per
-  // tile.  APC_RS_CH picks the chunk (default 10: profiles/r2*_rs_trace*.txt).
-  static const uint32_t ch_env = []() { const char* e = getenv("APC_RS_CH"); return e ? (uint32_t)atoi(e) : 10u; }();
+  // hypotheses per CTA (CH) and CTAs per SM.  CH = 20 / 16 with ONE CTA per SM (142 / 128 registers, the
+  // default), or CH = 10 / 8 with TWO (80 registers): the same arithmetic per SM.  Measured (APC_RS_CH=10,
+  // profiles/r2g_rs_trace_ch10.txt): the two co-resident CTAs share the issue slots, so a CTA's scoring
+  // phase does not shrink (8.6 vs 8.2 us), the kernel ends later (19.1 vs 16.1 us) and saturated throughput
+  // is the same (70.5 vs 71.2 us/scan): the larger chunk stays.
+  static const uint32_t ch_env = []() { const char* e = getenv("APC_RS_CH"); return e ? (uint32_t)atoi(e) : 20u; }();
   uint32_t ch;
   if (ch_env == 20 || ch_env == 16) {
     const uint32_t pad16 = apc_div_up(iters, 16) * 16, pad20 = apc_div_up(iters, 20) * 20;

@@ -43,10 +43,10 @@ __device__ __forceinline__ unsigned long long fixed_intensity(float w, ApcCtrl* 
 }
 
 // ITEMS points per thread, their atomics issued in lockstep (all key CAS first, then the probes of the
-// unlucky ones, then the joiners' accumulations).  ITEMS = 1 gives the shortest kernel when it runs
-// alone (more resident warps hide the dependent atomic chain); ITEMS = 4 holds a quarter of the threads
-// - and 40 % of the registers - for about the same time, which is what counts when eight lanes share the
-// register file (saturated throughput = sum of registers x time).  APC_VOX_ITEMS.
+// unlucky ones, then the joiners' accumulations).  ITEMS = 1 (default) gives the shortest kernel both
+// alone (15.7 vs 23.5 us: more resident warps hide the dependent atomic chain) and with eight lanes
+// sharing the GPU (68.9 vs 70.5 us/scan, profiles/r2g_knobs.json) although ITEMS = 4 holds half the
+// registers: the atomic round trips, not the register file, set this kernel's cost.  APC_VOX_ITEMS=4.
 template <int ITEMS>
 __global__ void __launch_bounds__(256)
 k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
@@ -264,7 +264,7 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
   {
     APC_PROF(ctx, "k_voxel_insert", s);
-    static const int items = []() { const char* e = getenv("APC_VOX_ITEMS"); return e ? atoi(e) : 4; }();
+    static const int items = []() { const char* e = getenv("APC_VOX_ITEMS"); return e ? atoi(e) : 1; }();
     if (items >= 4) {
       const uint32_t ib = min(apc_div_up(n_max, 1024), (uint32_t)APC_SM_COUNT * 8);
       k_voxel_insert<4><<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
@@ -307,38 +307,60 @@ extern "C" int apc_voxel_downsample(apc_ctx* ctx, const float* xyzi, uint32_t n_
                            nullptr, s);
 }
 
-// Per-attribute voxel mean, Open3D style: float32 sums (atomics), then sum / count in float32.
-__global__ void k_attr_zero(uint32_t n_max, const uint32_t* n_vox, float* sum, float* cnt) {
+// Per-attribute voxel mean (Open3D: attr.to(float32) -> index_add -> sum / count), made
+// ORDER-INDEPENDENT like the positions: every value is accumulated as the integer rint(v * 2^frac_bits)
+// (64-bit atomics), the mean is one float64 divide rounded to float32.  Deterministic whatever order the
+// atomics land in, bit-equal to oracle/voxel.py centroids_fixed(scale = 2^frac_bits); for integer-valued
+// attributes (ring, return_type, integer time stamps: frac_bits = 0) the sums are exact, which is also what
+// Open3D's float32 serial sum gives while it stays below 2^24.  |v * 2^frac_bits| must be < 2^40.
+struct AttrAcc {
+  long long sum;
+  uint32_t cnt;
+  uint32_t pad;
+};
+static_assert(sizeof(AttrAcc) == 16, "AttrAcc aliases the float4 scratch");
+__global__ void k_attr_zero(uint32_t n_max, const uint32_t* n_vox, AttrAcc* acc) {
   const uint32_t n = apc_count(n_vox, n_max);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { sum[i] = 0.f; cnt[i] = 0.f; }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    *reinterpret_cast<uint4*>(&acc[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
 __global__ void k_attr_add(const float* __restrict__ attr, const int32_t* __restrict__ p2v, uint32_t n_max,
-                           const uint32_t* n_dev, float* sum, float* cnt) {
+                           const uint32_t* n_dev, double scale, AttrAcc* acc, ApcCtrl* ctrl) {
   const uint32_t n = apc_count(n_dev, n_max);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int32_t v = p2v[i];
-    if (v >= 0) { atomicAdd(&sum[v], attr[i]); atomicAdd(&cnt[v], 1.0f); }
+    if (v < 0) continue;
+    const double q = __dmul_rn((double)attr[i], scale);
+    if (!(fabs(q) < 1099511627776.0)) {          // 2^40 (also rejects NaN / inf)
+      atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
+      continue;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&acc[v].sum), (unsigned long long)__double2ll_rn(q));
+    atomicAdd(&acc[v].cnt, 1u);
   }
 }
-__global__ void k_attr_div(uint32_t n_max, const uint32_t* n_vox, const float* __restrict__ sum,
-                           const float* __restrict__ cnt, float* __restrict__ out) {
+__global__ void k_attr_div(uint32_t n_max, const uint32_t* n_vox, const AttrAcc* __restrict__ acc, double inv_scale,
+                           float* __restrict__ out) {
   const uint32_t n = apc_count(n_vox, n_max);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = __fdiv_rn(sum[i], cnt[i]);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn(acc[i].sum), (double)acc[i].cnt), inv_scale));
 }
 
 extern "C" int apc_voxel_mean_attr(apc_ctx* ctx, const float* attr, const int32_t* p2v, uint32_t n_max,
-                                   const uint32_t* n_dev, const uint32_t* n_voxels_dev, float* out_attr, void* stream) {
+                                   const uint32_t* n_dev, const uint32_t* n_voxels_dev, int32_t frac_bits,
+                                   float* out_attr, void* stream) {
   if (!ctx) return APC_ERR_BAD_ARG;
   if (n_max == 0) return APC_OK;
   APC_REQUIRE(ctx, attr && p2v && out_attr, "NULL pointer");
   APC_REQUIRE(ctx, n_max <= ctx->max_points, "more points than the context was created for");
+  APC_REQUIRE(ctx, frac_bits >= 0 && frac_bits <= 30, "frac_bits must be in 0..30");
   cudaStream_t s = (cudaStream_t)stream;
-  float* sum = ctx->knn_avg;                               // scratch reuse: [max_points] floats each
-  float* cnt = reinterpret_cast<float*>(ctx->nb_count);
+  AttrAcc* acc = reinterpret_cast<AttrAcc*>(ctx->sorted_pts);   // scratch reuse: [max_points] x 16 bytes
+  const double scale = (double)(1u << frac_bits);
   const uint32_t blocks = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
-  k_attr_zero<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, sum, cnt);
-  k_attr_add<<<blocks, 256, 0, s>>>(attr, p2v, n_max, n_dev, sum, cnt);
-  k_attr_div<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, sum, cnt, out_attr);
+  k_attr_zero<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, acc);
+  k_attr_add<<<blocks, 256, 0, s>>>(attr, p2v, n_max, n_dev, scale, acc, ctx->ctrl);
+  k_attr_div<<<blocks, 256, 0, s>>>(n_max, n_voxels_dev, acc, 1.0 / scale, out_attr);
   APC_LAUNCH_CHECK(ctx, "k_attr_*");
   return APC_OK;
 }

@@ -265,10 +265,12 @@ class Context:
                                                  _ptr(vc), _ptr(cnt), _stream()))
         return out, vc, cnt
 
-    def voxel_mean_attr(self, attr_f32, p2v, n_voxels_dev, n_vox_max):
+    def voxel_mean_attr(self, attr_f32, p2v, n_voxels_dev, n_vox_max, frac_bits: int = 20):
+        """Order-independent voxel mean of one float32 attribute column (``apc_voxel_mean_attr``);
+        ``frac_bits`` from :func:`attr_frac_bits` of the attribute's own dtype."""
         out = self._empty((max(n_vox_max, 1),), torch.float32)
         self._ok(lib.apc_voxel_mean_attr(self.h, _ptr(attr_f32), _ptr(p2v), attr_f32.shape[0], None,
-                                         _ptr(n_voxels_dev), _ptr(out), _stream()))
+                                         _ptr(n_voxels_dev), int(frac_bits), _ptr(out), _stream()))
         return out
 
     # ---- outliers --------------------------------------------------------------------------------
@@ -393,6 +395,18 @@ class Context:
 
     def launch_graph(self, g):
         self._ok(lib.apc_graph_launch(self.h, g, _stream()))
+
+
+def attr_frac_bits(col: torch.Tensor) -> int:
+    """Fractional bits of the fixed-point voxel mean for an attribute column of dtype ``col.dtype``:
+    0 for integer attributes (exact sums), else as many as keep ``|v| * 2^bits`` below 2^39 (at most 20)."""
+    if not col.dtype.is_floating_point:
+        return 0
+    big = float(col.abs().nan_to_num(0.0, 0.0, 0.0).max().item()) if col.numel() else 0.0
+    bits = 20
+    while bits > 0 and big * (1 << bits) >= 2.0 ** 39:
+        bits -= 1
+    return bits
 
 
 def make_pipeline_maps(maps: dict) -> "_capi.PipelineMaps":

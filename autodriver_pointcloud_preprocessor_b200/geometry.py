@@ -387,7 +387,8 @@ class PointCloud:
             else:
                 # Open3D: attr.to(float32) -> index_add mean -> cast back to the attribute dtype
                 cols = src.reshape(n, -1)
-                outs = [ctx.voxel_mean_attr(cols[:, c].to(torch.float32).contiguous(), p2v, cnt, n)[:v]
+                fb = engine.attr_frac_bits(cols)
+                outs = [ctx.voxel_mean_attr(cols[:, c].to(torch.float32).contiguous(), p2v, cnt, n, fb)[:v]
                         for c in range(cols.shape[1])]
                 res = torch.stack(outs, 1).reshape((v,) + tuple(src.shape[1:])).to(src.dtype)
             attrs[k] = self._home(res)

@@ -448,7 +448,8 @@ class PointcloudPreprocessorNode(Node):
                 a = ctx.gather(col.contiguous(), maps['src_idx'], m_filt)
                 if self.voxel_size > 0.0:
                     mean = ctx.voxel_mean_attr(a.to(torch.float32).contiguous(), maps['p2v'],
-                                               counts[_capi.CNT_VOXELS:_capi.CNT_VOXELS + 1], m_filt)[:n_vox]
+                                               counts[_capi.CNT_VOXELS:_capi.CNT_VOXELS + 1], m_filt,
+                                               engine.attr_frac_bits(a))[:n_vox]
                     a = mean.to(col.dtype)
                 return ctx.gather(a.contiguous(), maps['out_row'], n_out)
 
@@ -609,8 +610,19 @@ class PointcloudPreprocessorNode(Node):
             src, attr = source.get(f.name, (0, None))
             out_fields.append((f.offset, f.datatype, src, attr))
         raw = ctx.repack(xyzi, out_fields, self.point_offset)
-        host = raw[:num_points * self.point_offset].cpu().numpy()
-        return np.frombuffer(host.tobytes(), dtype=dtype)
+        # ONE device -> host copy, into a pinned staging buffer that is kept across frames (two of them,
+        # alternating: the array handed out for frame k stays valid while frame k + 1 is prepared);
+        # create_cloud copies the records into the message (pp.py:769), so no further host copy is made
+        nbytes = num_points * self.point_offset
+        slot = self.frame_count & 1
+        stage = getattr(self, '_pinned_out', None)
+        if stage is None:
+            stage = self._pinned_out = [None, None]
+        if stage[slot] is None or stage[slot].numel() < nbytes:
+            stage[slot] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        stage[slot][:nbytes].copy_(raw[:nbytes], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return np.frombuffer(stage[slot].numpy(), dtype=dtype, count=num_points)
 
     def create_header(self, ros_cloud, frame_id=None):
         """pp.py:628-641."""

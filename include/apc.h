@@ -214,11 +214,15 @@ int apc_voxel_downsample_sorted(apc_ctx* ctx, const float* xyzi, uint32_t n_max,
                                 float voxel_size, float* out_xyzi, uint32_t* out_voxel_counts,
                                 uint32_t* out_count_dev, void* stream);
 
-/* Per-attribute voxel mean "in float32 then cast back" (Open3D index_add per attribute,
- * SURVEY.md B7) for a float32 attribute, using p2v / counts from apc_voxel_downsample. */
+/* Per-attribute voxel mean (Open3D index_add per attribute then sum / count; the caller
+ * casts the result back to the attribute's dtype, pp.py:511) for a float32 attribute array, using p2v /
+ * counts from apc_voxel_downsample or apc_pipeline_run_maps.  Order-independent like the positions:
+ * values are accumulated as rint(v * 2^frac_bits) in 64-bit integers, the mean is one float64 divide
+ * rounded to float32.  frac_bits = 0 for integer-valued attributes (ring, return_type: exact), up to 30
+ * for real-valued ones; |v * 2^frac_bits| must stay below 2^40 (APC_ERR_KEY_RANGE at apc_check). */
 int apc_voxel_mean_attr(apc_ctx* ctx, const float* attr, const int32_t* p2v, uint32_t n_max,
-                        const uint32_t* n_dev, const uint32_t* n_voxels_dev, float* out_attr,
-                        void* stream);
+                        const uint32_t* n_dev, const uint32_t* n_voxels_dev, int32_t frac_bits,
+                        float* out_attr, void* stream);
 
 /* ---- (5) outlier removal ----------------------------------------------------------- */
 

@@ -75,10 +75,21 @@ def test_carrier_ops_against_oracle(golden_dir):
     ref = voxel.voxel_down_sample(ref_pos[m], 0.25, scan["intensity"][keep][m], fixed=True)
     assert np.array_equal(v.point.positions.cpu().numpy().view(np.uint32), ref["positions"].view(np.uint32))
     assert np.array_equal(v.point.intensity.cpu().numpy().reshape(-1).view(np.uint32), ref["intensity"].view(np.uint32))
-    ring_ref = voxel.centroids_o3d(scan["ring"][keep][m].astype(np.float32), ref["p2v"], ref["counts"].size)
+    # ring (uint16): exact integer sums, one divide, cast back - bit-equal to the oracle's fixed-point mean
+    # AND to Open3D's float32 serial index_add (the sums stay far below 2^24)
+    nv = ref["counts"].size
+    ring_in = scan["ring"][keep][m].astype(np.float32)
     got_ring = v.point.ring.cpu().numpy().reshape(-1)
     assert got_ring.dtype == np.uint16
-    assert np.max(np.abs(got_ring.astype(np.float64) - ring_ref.astype(np.uint16))) <= 1      # float32 atomics order
+    assert np.array_equal(got_ring, voxel.centroids_fixed(ring_in, ref["p2v"], nv, scale=1.0).astype(np.uint16))
+    assert np.array_equal(got_ring, voxel.centroids_o3d(ring_in, ref["p2v"], nv).astype(np.uint16))
+    # time (float64 in the carrier, averaged in float32): order-independent 2^-20 fixed point, bit-equal to
+    # the oracle; within 1e-6 of Open3D's float32 serial sum
+    time_in = scan["time"][keep][m].astype(np.float32)
+    got_time = v.point.time.cpu().numpy().reshape(-1)
+    assert got_time.dtype == np.float64
+    assert np.array_equal(got_time, voxel.centroids_fixed(time_in, ref["p2v"], nv, scale=float(1 << 20)).astype(np.float64))
+    assert np.allclose(got_time, voxel.centroids_o3d(time_in, ref["p2v"], nv), rtol=0, atol=1e-6)
     # select_by_index(invert=True) == complement in order (pp.py:542)
     idx = o3d.Tensor(torch.tensor([0, 5, 7], dtype=torch.int64))
     rest = v.select_by_index(idx, invert=True)
@@ -234,9 +245,9 @@ def test_node_callback_with_normals_and_reference_backends(layout, fused, backen
 
 def test_fused_and_staged_paths_publish_the_same_cloud():
     """Velodyne-style layout (x, y, z, intensity, ring u16, time f32): the fused pipeline (attributes
-    carried through its index maps) and the staged carrier path publish the same message - positions
-    and intensity bit-equal; ring / time are float32 voxel means accumulated with atomics in both
-    paths, so they agree to the last float32 bit or so (ring within 1 after the cast back)."""
+    carried through its index maps) and the staged carrier path publish the same message, byte for
+    byte - the attribute voxel means are order-independent fixed-point sums in both paths - and the
+    attributes equal the oracle's (``oracle.voxel.centroids_fixed`` over the oracle's own voxel map)."""
     from oracle import pc2
     scan, msg = scan_msg("xyzirt22", seed=49, n_beams=32, n_az=1024)
     outs = {}
@@ -249,13 +260,29 @@ def test_fused_and_staged_paths_publish_the_same_cloud():
         outs[fused] = np.frombuffer(out.data, dtype=pc2.dtype_from_fields(out.fields, out.point_step))
     a, b = outs["true"], outs["false"]
     assert a.shape == b.shape and a.dtype == b.dtype
-    for k in ("x", "y", "z", "intensity"):
-        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
-    assert a["ring"].any() and np.max(np.abs(a["ring"].astype(np.int64) - b["ring"].astype(np.int64))) <= 1
-    assert np.allclose(a["time"], b["time"], rtol=1e-5, atol=1e-7)
-    # single-point voxels carry the input's attribute values exactly: most of the cloud at 0.1 m
-    exact = (a["ring"] == b["ring"]).mean()
-    assert exact > 0.95
+    assert a["ring"].any()
+    assert a.tobytes() == b.tobytes()
+    # against the oracle: pipeline with the same stages, attributes averaged over ITS point -> voxel map
+    from oracle import pipeline as opipe
+    from oracle import voxel
+    cfg = opipe.default_config()
+    cfg.update(voxel_size=0.1, radius=dict(nb_points=node.remove_radius_outliers_nb_points,
+                                           radius=node.remove_radius_outliers_search_radius),
+               ground=dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=3))
+    ref = opipe.preprocess(msg, cfg)
+    assert a.shape[0] == ref["positions"].shape[0]
+    assert np.array_equal(np.stack([a["x"], a["y"], a["z"]], 1).view(np.uint32), ref["positions"].view(np.uint32))
+    nv = ref["voxel_counts"].size
+    keep = ref["radius_mask"].copy()
+    rows = np.flatnonzero(keep)
+    ground = np.ones(rows.size, dtype=bool)
+    ground[ref["ground_inliers"]] = False
+    rows = rows[ground]                                            # voxel rows that reach the output, in order
+    ring_in = scan["ring"][ref["src_idx"]].astype(np.float32)
+    time_in = scan["time"][ref["src_idx"]].astype(np.float32)
+    assert np.array_equal(a["ring"], voxel.centroids_fixed(ring_in, ref["p2v"], nv, scale=1.0).astype(np.uint16)[rows])
+    assert np.array_equal(a["time"].view(np.uint32),
+                          voxel.centroids_fixed(time_in, ref["p2v"], nv, scale=float(1 << 20))[rows].view(np.uint32))
 
 
 def test_node_saves_published_cloud_as_pcd(tmp_path):
