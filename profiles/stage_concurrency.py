@@ -5,6 +5,10 @@ difference between consecutive rows is what a stage costs at that level of concu
 overlaps perfectly halves with every doubling of the lanes; one bound by a shared resource stays flat.
 
     python profiles/stage_concurrency.py OUT.json
+
+SHARED_STREAM=1: all lanes share one stream, so the scans run strictly one after the other while their
+hash tables alternate between the lanes' contexts - the same serial execution as one lane, minus the
+L2 residency of the tables.  N_CONFIGS / LANE_SET restrict the sweep.
 """
 import json
 import os
@@ -36,6 +40,9 @@ for name, stages in configs:
     row = {}
     for lanes in lane_set:
         pipe = replay.ScanPipeline(msg0.fields, bench.POINT_STEP, bench.N_POINTS, filter_kw, stages, lanes=lanes, device=0)
+        if os.environ.get("SHARED_STREAM") == "1":      # L2-residency probe: the lanes' contexts (tables) alternate
+            for ln in pipe.lanes[1:]:                   # frame by frame, but everything runs on ONE stream
+                ln.stream = pipe.lanes[0].stream
         counts = torch.zeros((F, 8), dtype=torch.int32, device=dev)
         pipe.prepare_resident(pool, None, counts)
         ids = list(range(F))

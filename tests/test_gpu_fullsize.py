@@ -158,3 +158,74 @@ def test_c5_batched_replay_matches_single_shot(big):
         assert n == want[f].shape[0]
         assert np.array_equal(slab[f, :n].cpu().numpy().view(np.uint32), want[f].view(np.uint32)), f
     pipe.close()
+
+
+def test_c1_full_size_131072_crop_voxel_ground(big):
+    """configs[0] at its own size: 64 x 2048 = 131 072 points, crop_box + 0.1 m voxels + RANSAC ground
+    removal, every intermediate count and the published rows bit-exact against the oracle."""
+    import bench
+    from oracle import pipeline as opipe
+    ctx, engine, capi, synth = big["ctx"], big["engine"], big["capi"], big["synth"]
+    msg = synth.pack_cloud(synth.lidar_scan(seed=64, n_beams=64, n_az=2048), "xyzi16")
+    assert msg.width == 131072
+    desc = engine.make_cloud_desc(msg.fields, msg.point_step, msg.width, dev_bytes(msg))
+    ground = dict(distance_threshold=0.2, ransac_n=5, num_iterations=100, probability=0.99, seed=7)
+    fcfg = engine.make_filter_cfg(skip_nans=True, dedup_mode=capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True,
+                                  crop=bench.CROP)
+    out, counts, plane = ctx.pipeline_run([desc], engine.make_pipeline_cfg(fcfg, voxel_size=0.1, ground=ground))
+    ctx.check()
+    cfg = opipe.default_config()
+    cfg.update(crop=bench.CROP, voxel_size=0.1, ground=ground)
+    ref = opipe.preprocess(msg, cfg)
+    c = counts.cpu().numpy()
+    assert c[capi.CNT_INPUT] == 131072 and c[capi.CNT_FILTERED] == ref["n_filtered"]
+    assert c[capi.CNT_VOXELS] == ref["voxel_positions"].shape[0]
+    assert c[capi.CNT_GROUND_INLIERS] == ref["ground_inliers"].size
+    n = int(c[capi.CNT_OUTPUT])
+    assert n == ref["positions"].shape[0]
+    got = out[:n].cpu().numpy()
+    assert np.array_equal(got[:, :3].view(np.uint32), ref["positions"].view(np.uint32))
+    assert np.array_equal(got[:, 3].view(np.uint32), ref["intensity"].view(np.uint32))
+    assert np.allclose(plane.cpu().numpy()[:4], ref["plane"], atol=1e-5, rtol=0)
+
+
+def test_concat_eight_sensors_at_the_cloud_limit(big):
+    """APC_MAX_CLOUDS = 8 sensors of three byte layouts, ragged sizes (one empty), each with its own
+    extrinsic, merged in one launch and voxelised: sensor order and point order preserved."""
+    from oracle import pipeline as opipe
+    from oracle import voxel
+    ctx, engine, capi, synth = big["ctx"], big["engine"], big["capi"], big["synth"]
+    layouts = ["xyzi16", "xyzirt22", "ouster48", "xyzi16", "xyzirt22", "ouster48", "xyzi16", "xyzirt22"]
+    sizes = [(32, 1024), (16, 777), (8, 1), (64, 512), (32, 333), (16, 1024), (128, 256), (32, 1025)]
+    T = np.concatenate([synth.sensor_extrinsics(4), synth.sensor_extrinsics(4)])
+    T[4:, :3, 3] += np.array([3.0, -2.0, 0.5], dtype=np.float32)
+    scans, msgs = [], []
+    for s, ((nb, na), lay) in enumerate(zip(sizes, layouts)):
+        sc = synth.lidar_scan(seed=200 + s, n_beams=nb, n_az=na, nan_frac=0.0, dup_frac=0.0)
+        if s == 2:                                              # an empty sensor in the middle
+            sc = {k: v[:0] for k, v in sc.items()}
+        scans.append(sc)
+        msgs.append(synth.pack_cloud(sc, lay))
+    bufs = [dev_bytes(m) if m.width else torch.zeros(16, dtype=torch.uint8, device="cuda") for m in msgs]
+    descs = [engine.make_cloud_desc(m.fields, m.point_step, m.width, b, transform=T[s])
+             for s, (m, b) in enumerate(zip(msgs, bufs))]
+    assert len(descs) == capi.APC_MAX_CLOUDS
+    fcfg = engine.make_filter_cfg()
+    xyzi, src, _, cnt = ctx.frontend(descs, fcfg, want_src=True)
+    ctx.check()
+    merged = opipe.concat(scans, list(T))
+    n = int(cnt.item())
+    assert n == merged["positions"].shape[0] == sum(m.width for m in msgs)
+    got = xyzi[:n].cpu().numpy()
+    assert np.array_equal(got[:, :3].view(np.uint32), merged["positions"].view(np.uint32))
+    assert np.array_equal(got[:, 3].view(np.uint32), merged["intensity"].view(np.uint32))
+    assert np.array_equal(src[:n].cpu().numpy(), np.arange(n))
+    out, counts, _ = ctx.pipeline_run(descs, engine.make_pipeline_cfg(fcfg, voxel_size=0.1))
+    ctx.check()
+    ref = voxel.voxel_down_sample(merged["positions"], 0.1, merged["intensity"], fixed=True)
+    v = int(counts.cpu().numpy()[capi.CNT_OUTPUT])
+    assert v == ref["positions"].shape[0]
+    assert np.array_equal(out[:v].cpu().numpy()[:, :3].view(np.uint32), ref["positions"].view(np.uint32))
+    # a ninth sensor is refused
+    with pytest.raises(capi.ApcError):
+        ctx.frontend(descs + [descs[0]], fcfg, want_src=False)
