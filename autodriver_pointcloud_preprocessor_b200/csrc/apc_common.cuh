@@ -20,26 +20,28 @@ enum { APC_DEVERR_KEY_RANGE = 1u, APC_DEVERR_CAPACITY = 2u };
 
 #define APC_NUM_SCAN_STATES 8
 
-// One voxel of the open-addressing table, split in two 32-byte halves kept in separate arrays.
-// VoxSlot ("hot") is everything a single-point voxel ever touches (77 % of the voxels of a 0.1 m C2
-// scan): the point whose CAS claims the slot (the "owner") records its index with a plain store and
-// its coordinates are added when the voxel is finalised.  Only the points that JOIN an existing voxel
-// pay the accumulating atomics (0.7 M per scan instead of 1.8 M), which land in VoxAcc ("cold").
+// One voxel of the open-addressing table, split in a 16-byte HOT slot and a 48-byte COLD record kept in
+// separate arrays.  The hot slot is everything a single-point voxel ever touches (77 % of the voxels of a
+// 0.1 m C2 scan): the point whose CAS claims the slot (the "owner") records its index with a plain store
+// and its coordinates are added when the voxel is finalised.  Only the points that JOIN an existing voxel
+// pay the accumulating atomics (0.7 M per scan instead of 1.8 M), which land in the cold record.
 // Placement keeps neighbours together: the slot index is hash(2x2 block of voxels in x, y) * 4 + the
-// voxel's position inside the block, so the four slots of a 128-byte line (two 64-byte DRAM bursts)
-// belong to spatially adjacent voxels - a surface fills 2 to 4 of them instead of 1, which halves
-// the table's DRAM traffic (it is read and written back twice per scan, by insert and finalize).
-struct __align__(32) VoxSlot {
+// voxel's position inside the block, so the four voxels of a block share ONE 64-byte DRAM burst (two
+// 32-byte sectors) and eight share a 128-byte line - a surface fills 2 to 4 of a block's slots.  Round 1
+// used 32-byte hot slots (one sector per voxel, two per burst): the table is random-access traffic, read
+// and written back by both the insert and the finalize kernel, and at 1 M points it IS the voxel stage's
+// DRAM traffic (178 B per point against 36 B algorithmic, profiles/r2d_voxel_ab_ncu.csv).
+struct __align__(16) VoxSlot {
   unsigned long long key;     // packed 63-bit voxel key, all ones = empty
   uint32_t first;             // lowest index among the JOINING points (0xffffffff: none)
-  uint32_t cnt;               // number of joining points (the owner is not counted)
   uint32_t owner;             // index of the point that claimed the slot
+};
+struct __align__(16) VoxAcc {
+  unsigned long long acc[4];  // fixed-point sums over the joining points: x, y, z (2^-24 m), intensity (2^-20)
+  uint32_t cnt;               // number of joining points (the owner is not counted)
   uint32_t pad[3];
 };
-struct __align__(32) VoxAcc {
-  unsigned long long acc[4];  // fixed-point sums over the joining points: x, y, z (2^-24 m), intensity (2^-20)
-};
-static_assert(sizeof(VoxSlot) == 32 && sizeof(VoxAcc) == 32, "voxel slots are one 32-byte sector each");
+static_assert(sizeof(VoxSlot) == 16 && sizeof(VoxAcc) == 48, "voxel table layout");
 
 // Optional per-kernel timing with CUDA events on the launching stream (apc_profile_*).
 struct ApcProf {
@@ -59,8 +61,8 @@ struct apc_ctx {
   uint32_t max_tiles = 0;
   // hash tables (capacity = power of two >= 2*max_points)
   uint32_t hash_cap = 0;
-  struct VoxSlot* vox_slots = nullptr;  // [hash_cap] hot halves {key, first, cnt, owner}
-  struct VoxAcc* vox_acc = nullptr;     // [hash_cap] cold halves: fixed-point sums of the joining points
+  struct VoxSlot* vox_slots = nullptr;  // [hash_cap] hot slots {key, first, owner}
+  struct VoxAcc* vox_acc = nullptr;     // [hash_cap] cold records: fixed-point sums + count of the joining points
   uint32_t* vox_rank = nullptr;     // [hash_cap] output row of the slot
   uint32_t* p2slot = nullptr;       // [max_points]
   unsigned long long* dedup_slots = nullptr;  // [hash_cap] {key fingerprint:32 | lowest point index:32}
@@ -164,6 +166,18 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// 128-bit relaxed accesses at gpu scope: a 16-byte aligned vector access is performed as one transaction,
+// and the qualifier keeps the compiler from splitting, caching or re-ordering it against the other CTAs'
+// accesses to the same slot (voxel.cu: slots are cleaned by one CTA while others still read them).
+__device__ __forceinline__ uint4 ld_relaxed_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u4(void* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // "Last CTA" ticket: called by ONE thread after a __syncthreads().  The acq_rel RMW at gpu scope

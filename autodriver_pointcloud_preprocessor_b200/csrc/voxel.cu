@@ -2,8 +2,8 @@
 //
 // Replaces Open3D t.PointCloud.voxel_down_sample (pp.py:509-512).
 //   key       = floor(float32(x) / float32(voxel_size)) per axis, 21 bits each (+2^20 bias)
-//   table     = open addressing, 64-bit atomicCAS on the key word; 2x2 (x, y) blocks of voxels share
-//               a 128-byte line of four 32-byte slots, probing moves block by block (see VoxSlot)
+//   table     = open addressing, 64-bit atomicCAS on the key word of a 16-byte hot slot; the four voxels
+//               of a 2x2 (x, y) block share one 64-byte burst, probing moves block by block (see VoxSlot)
 //   centroid  = order-independent fixed-point sums (rint(x*2^24), 64-bit integer atomics) so
 //               the result is deterministic and bit-identical to oracle/voxel.py
 //               centroids_fixed whatever order the atomics land in; the point that claims a
@@ -104,8 +104,8 @@ k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n
       } else if (old[j] == key[j]) {      // joins an existing voxel
         p2slot[i] = slot[j];
         atomicMin(&s->first, i);
-        atomicAdd(&s->cnt, 1u);
         VoxAcc* a = &accs[slot[j]];
+        atomicAdd(&a->cnt, 1u);
         atomicAdd(&a->acc[0], fixed_xyz(p[j].x));
         atomicAdd(&a->acc[1], fixed_xyz(p[j].y));
         atomicAdd(&a->acc[2], fixed_xyz(p[j].z));
@@ -150,17 +150,9 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
     const uint32_t i = tile * APC_TILE_POINTS + j * APC_TILE_THREADS + threadIdx.x;
     slot[j] = i < n ? p2slot[i] : VOX_NOSLOT;
   }
-  uint32_t owner[APC_TILE_ITEMS];
 #pragma unroll
-  for (int j = 0; j < APC_TILE_ITEMS; ++j) {   // sector 0 = {key lo, key hi, first, cnt | owner, pad}: all loads in flight
-    head[j] = make_uint4(0u, 0u, 0u, 0u);
-    owner[j] = 0u;
-    if (slot[j] != VOX_NOSLOT) {
-      const uint4* raw = reinterpret_cast<const uint4*>(&slots[slot[j]]);
-      head[j] = raw[0];
-      owner[j] = raw[1].x;
-    }
-  }
+  for (int j = 0; j < APC_TILE_ITEMS; ++j)     // the whole hot slot {key lo, key hi, first, owner} in one load: all in flight
+    head[j] = slot[j] != VOX_NOSLOT ? ld_relaxed_u4(&slots[slot[j]]) : make_uint4(0u, 0u, 0u, 0u);
   float4 cen[APC_TILE_ITEMS];
   uint32_t npts[APC_TILE_ITEMS];
   uint32_t gslot[APC_TILE_ITEMS], grank[APC_TILE_ITEMS];
@@ -170,16 +162,17 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
     // a slot whose key already reads empty was finalised (and cleaned) by an earlier tile: this
     // point is then certainly not the first of its voxel
     is_first[j] = slot[j] != VOX_NOSLOT && !(head[j].x == 0xffffffffu && head[j].y == 0xffffffffu) &&
-                  i == min(head[j].z, owner[j]);
+                  i == min(head[j].z, head[j].w);
+    npts[j] = 1u;
     if (is_first[j]) {
-      const float4 po = pts[owner[j]];   // mostly i itself: 3 voxels in 4 hold one point
+      const float4 po = pts[head[j].w];   // the owner - mostly i itself: 3 voxels in 4 hold one point
       ulonglong2 a01 = make_ulonglong2(0ull, 0ull), a23 = make_ulonglong2(0ull, 0ull);
-      if (head[j].w) {                   // sums exist only when somebody joined: the cold half is not read otherwise
+      if (head[j].z != 0xffffffffu) {     // somebody joined: sums and their count live in the cold record
         const uint4* raw = reinterpret_cast<const uint4*>(&accs[slot[j]]);
         a01 = *reinterpret_cast<const ulonglong2*>(&raw[0]);
         a23 = *reinterpret_cast<const ulonglong2*>(&raw[1]);
+        npts[j] = raw[2].x + 1u;
       }
-      npts[j] = head[j].w + 1u;
       const double dc = (double)npts[j];
       cen[j] = make_float4(fixed_mean(a01.x + fixed_xyz(po.x), dc, 1.0 / 16777216.0),
                            fixed_mean(a01.y + fixed_xyz(po.y), dc, 1.0 / 16777216.0),
@@ -209,13 +202,14 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
       }
       if (out_counts) out_counts[r] = npts[j];
       if (rank_of_slot) rank_of_slot[s] = r;   // only the point->voxel map needs it (a scattered 4-byte store per voxel)
-      // self-clean the slot for the next frame: {key = empty, first = max, cnt = 0}; the sums only
-      // where they were written
-      *reinterpret_cast<uint4*>(&slots[s]) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      // self-clean the slot for the next frame: {key = empty, first = none, owner = 0}; the cold record
+      // only where it was written
+      st_relaxed_u4(&slots[s], make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u));
       if (npts[j] > 1u) {
         uint4* raw = reinterpret_cast<uint4*>(&accs[s]);
         raw[0] = make_uint4(0u, 0u, 0u, 0u);
         raw[1] = make_uint4(0u, 0u, 0u, 0u);
+        raw[2] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
@@ -234,12 +228,11 @@ __global__ void k_voxel_p2v(uint32_t n_max, const uint32_t* n_dev, const uint32_
 // Whole-table reset (context creation and error recovery only).
 __global__ void k_voxel_reset(VoxSlot* slots, VoxAcc* accs, uint32_t cap) {
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
-    uint4* raw = reinterpret_cast<uint4*>(&slots[s]);
-    raw[0] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-    raw[1] = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(&slots[s]) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
     uint4* acc = reinterpret_cast<uint4*>(&accs[s]);
     acc[0] = make_uint4(0u, 0u, 0u, 0u);
     acc[1] = make_uint4(0u, 0u, 0u, 0u);
+    acc[2] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
