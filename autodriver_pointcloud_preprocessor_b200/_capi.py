@@ -81,6 +81,7 @@ def _load():
         "apc_ctx_create": [i32, u32, C.POINTER(vp)],
         "apc_ctx_destroy": [vp],
         "apc_check": [vp, vp],
+        "apc_ctx_set_low_latency": [vp, i32],
         "apc_version": [],
         "apc_frontend": [vp, C.POINTER(CloudDesc), u32, C.POINTER(FilterCfg), vp, vp, vp, vp, vp],
         "apc_unpack": [vp, C.POINTER(CloudDesc), vp, vp],
@@ -135,7 +136,7 @@ def _load():
 lib = _load()
 
 #: every symbol include/apc.h declares (checked by tests/test_capi_symbols.py)
-SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_last_error", "apc_check", "apc_version",
+SYMBOLS = ["apc_ctx_create", "apc_ctx_destroy", "apc_ctx_set_low_latency", "apc_last_error", "apc_check", "apc_version",
            "apc_ctx_max_points", "apc_frontend", "apc_unpack", "apc_transform", "apc_crop_mask",
            "apc_non_finite_mask", "apc_duplicate_mask", "apc_unique_rows", "apc_select_by_mask", "apc_gather",
            "apc_voxel_downsample", "apc_voxel_downsample_sorted", "apc_voxel_mean_attr", "apc_radius_outliers",

@@ -92,6 +92,7 @@ struct apc_ctx {
   uint32_t* sort_idx = nullptr;     // [max_points] first-index / inverse list of the pipeline's sort modes
   float* nrm_scratch = nullptr;     // [3 * max_points] normals of the cloud entering the ground stage (pipeline), on first use
   struct NeighborScratch* neighbors = nullptr;   // neighbour grids + KNN scratch (neighbors.cu), on first use
+  bool low_latency = false;         // apc_ctx_set_low_latency: programmatic dependent launches on the pipeline path
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.
@@ -144,6 +145,39 @@ int apc_begin(apc_ctx* ctx, cudaStream_t s);
   } while (0)
 
 static inline uint32_t apc_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Kernel launch of the per-scan path.  In low-latency mode (one scan in flight: the ROS node, pp.py:1056)
+// every launch carries the programmatic-stream-serialization attribute: the next kernel of the chain is
+// set up and its CTAs made resident while the current one still runs, and starts computing the moment
+// the current one has completed and flushed (griddepcontrol.wait at the top of every such kernel),
+// instead of paying a launch latency of ~3 us per stage boundary, 13 times per scan.  Off by default:
+// with eight lanes sharing the GPU the pre-launched, waiting CTAs would only take room from the other
+// lanes' kernels.  Errors are picked up by the APC_LAUNCH_CHECK that follows the call.
+#ifdef __CUDACC__
+template <typename... P, typename... A>
+static inline void apc_klaunch(const apc_ctx* ctx, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  if (ctx->low_latency) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+// First statement of every kernel launched through apc_klaunch: wait for the preceding kernel's results
+// (a no-op for an ordinary launch), then let the following kernel be set up behind this one.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 // ---- device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -36,6 +36,7 @@ int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce) {
 }
 
 __global__ void k_begin(ApcCtrl* ctrl) {
+  pdl_enter();
   APC_STAMP(0, 0);
   if (threadIdx.x == 0) ctrl->epoch = ctrl->epoch + 1u;
   if (threadIdx.x < 30) ctrl->counters[threadIdx.x] = 0u;
@@ -45,7 +46,7 @@ int apc_begin(apc_ctx* ctx, cudaStream_t s) {
   int cur = -1;
   if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device)
     return apc_set_error(ctx, APC_ERR_BAD_ARG, "the context lives on another device than the calling thread's current one");
-  k_begin<<<1, 32, 0, s>>>(ctx->ctrl);
+  apc_klaunch(ctx, k_begin, 1, 32, 0, s, ctx->ctrl);
   APC_LAUNCH_CHECK(ctx, "k_begin");
   return APC_OK;
 }
@@ -147,6 +148,12 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   A(cudaDeviceSynchronize());
 #undef A
   *out = ctx;
+  return APC_OK;
+}
+
+extern "C" int apc_ctx_set_low_latency(apc_ctx* ctx, int on) {
+  if (!ctx) return APC_ERR_BAD_ARG;
+  ctx->low_latency = on != 0;
   return APC_OK;
 }
 

@@ -130,6 +130,7 @@ template <bool GENERIC>
 __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_constant__ FrontendParams prm) {
   extern __shared__ __align__(16) uint8_t stage[];
   __shared__ __align__(8) uint64_t bar;
+  pdl_enter();
   const uint32_t tile = blockIdx.x;
   const uint32_t si = find_segment(prm, tile);
   const SegDev& s = prm.seg[si];
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
   extern __shared__ __align__(16) uint8_t stage[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t sm_scan[34];
+  pdl_enter();
   const uint32_t tile = blockIdx.x;
   const uint32_t si = find_segment(prm, tile);
   const SegDev& s = prm.seg[si];
@@ -496,13 +498,13 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
   const bool generic = smem != 0;   // some segment needs the byte-record decoder
   if (prm.dedup) {
     APC_PROF(ctx, "k_dedup_insert", s);
-    if (generic) k_dedup_insert<true><<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
-    else k_dedup_insert<false><<<prm.n_tiles, APC_TILE_THREADS, 0, s>>>(prm);
+    if (generic) apc_klaunch(ctx, k_dedup_insert<true>, prm.n_tiles, APC_TILE_THREADS, smem, s, prm);
+    else apc_klaunch(ctx, k_dedup_insert<false>, prm.n_tiles, APC_TILE_THREADS, 0, s, prm);
     APC_LAUNCH_CHECK(ctx, "k_dedup_insert");
   }
   APC_PROF(ctx, "k_frontend", s);
-  if (generic) k_frontend<true><<<prm.n_tiles, APC_TILE_THREADS, smem, s>>>(prm);
-  else k_frontend<false><<<prm.n_tiles, APC_TILE_THREADS, 0, s>>>(prm);
+  if (generic) apc_klaunch(ctx, k_frontend<true>, prm.n_tiles, APC_TILE_THREADS, smem, s, prm);
+  else apc_klaunch(ctx, k_frontend<false>, prm.n_tiles, APC_TILE_THREADS, 0, s, prm);
   APC_LAUNCH_CHECK(ctx, "k_frontend");
   return APC_OK;
 }
@@ -682,6 +684,7 @@ k_select_by_mask(const float4* __restrict__ in, uint32_t n_max, const uint32_t* 
                  uint64_t* scan_state, const ApcCtrl* ctrl, uint32_t n_tiles, const uint32_t* __restrict__ idx_in,
                  const __grid_constant__ MirrorDev mir) {
   __shared__ uint32_t sm_scan[34];
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
   const uint32_t tile = blockIdx.x;
@@ -730,7 +733,7 @@ int apc_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
   APC_PROF(ctx, "k_select_by_mask", s);
-  k_select_by_mask<<<n_tiles, APC_TILE_THREADS, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, mask, invert,
+  apc_klaunch(ctx, k_select_by_mask, n_tiles, APC_TILE_THREADS, 0, s, reinterpret_cast<const float4*>(xyzi), n_max, n_dev, mask, invert,
                                                         reinterpret_cast<float4*>(out_xyzi), out_idx, out_count_dev,
                                                         ctx->scan_state[scan_slot], ctx->ctrl, n_tiles, idx_in,
                                                         mir ? *mir : MirrorDev{});

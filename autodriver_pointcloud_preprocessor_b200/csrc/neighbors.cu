@@ -62,6 +62,7 @@ __device__ __forceinline__ bool grid_lookup(const GridDev& g, uint64_t key, uint
 // (k_grid_insert over 12 levels of a 586 k-point cloud: 516 -> see profiles/config_times.py).
 __global__ void __launch_bounds__(256)
 k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
   const float c = grid_cell_size(g, level);
@@ -109,6 +110,7 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
 // rank-0 points reserve a contiguous run for their cell (warp-aggregated cursor bump)
 __global__ void __launch_bounds__(256)
 k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
   const uint32_t lane = lane_id();
@@ -141,6 +143,7 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
 
 __global__ void __launch_bounds__(256)
 k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g) {
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t level = blockIdx.y;
   APC_STAMP(3, 0);
@@ -237,6 +240,7 @@ __device__ __forceinline__ uint32_t radius_count(const GridDev& g, float c, floa
 __global__ void __launch_bounds__(128)
 k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32_t nb_points, int need_counts,
                uint8_t* __restrict__ mask, uint32_t* __restrict__ counts, const ApcCtrl* __restrict__ ctrl) {
+  pdl_enter();
   const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
   const float c = grid_cell_size(g, 0);
   APC_STAMP(0, 0);
@@ -303,7 +307,7 @@ static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const u
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   if (!split) {
     APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    apc_klaunch(ctx, k_radius_query, bq, 128, 0, s, n_max, n_dev, g, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
     APC_LAUNCH_CHECK(ctx, "k_radius_query");
     return APC_OK;
   }
@@ -749,14 +753,14 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
   const dim3 grid(bx, g.d.levels);
   if (!inserted) {   // (the pipeline's voxel stage inserts its centroids as it writes them)
     APC_PROF(ctx, "k_grid_insert", s);
-    k_grid_insert<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d, ctx->ctrl);
+    apc_klaunch(ctx, k_grid_insert, grid, 256, 0, s, pts, n_max, n_dev, g.d, ctx->ctrl);
   }
   {
     APC_PROF(ctx, "k_grid_assign", s);
-    k_grid_assign<<<grid, 256, 0, s>>>(n_max, n_dev, g.d, ctx->ctrl);
+    apc_klaunch(ctx, k_grid_assign, grid, 256, 0, s, n_max, n_dev, g.d, ctx->ctrl);
   }
   APC_PROF(ctx, "k_grid_scatter", s);
-  k_grid_scatter<<<grid, 256, 0, s>>>(pts, n_max, n_dev, g.d);
+  apc_klaunch(ctx, k_grid_scatter, grid, 256, 0, s, pts, n_max, n_dev, g.d);
   APC_LAUNCH_CHECK(ctx, "grid_build");
   return APC_OK;
 }
@@ -782,7 +786,7 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   if (out_counts) {
     const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
     APC_PROF(ctx, "k_radius_query", s);
-    k_radius_query<<<bq, 128, 0, s>>>(n_max, n_dev, g.d, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
+    apc_klaunch(ctx, k_radius_query, bq, 128, 0, s, n_max, n_dev, g.d, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
   } else {
     rc = radius_decide(ctx, g.d, n_max, n_dev, r2, (uint32_t)nb_points, out_mask, s);
     if (rc) return rc;
@@ -803,6 +807,7 @@ k_radius_select(const float4* __restrict__ in, uint32_t n_max, const uint32_t* n
                 uint32_t n_tiles, const uint32_t* __restrict__ idx_in, uint32_t* __restrict__ out_idx,
                 const __grid_constant__ MirrorDev mir) {
   __shared__ uint32_t sm_scan[34];
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
   const uint32_t tile = blockIdx.x;
@@ -873,7 +878,7 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");
   APC_PROF(ctx, "k_radius_select", s);
-  k_radius_select<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, mask_scratch, g.d, reinterpret_cast<float4*>(out_xyzi),
+  apc_klaunch(ctx, k_radius_select, n_tiles, APC_TILE_THREADS, 0, s, pts, n_max, n_dev, mask_scratch, g.d, reinterpret_cast<float4*>(out_xyzi),
                                                        out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl, n_tiles,
                                                        idx_in, out_idx, mir ? *mir : MirrorDev{});
   APC_LAUNCH_CHECK(ctx, "radius_select");

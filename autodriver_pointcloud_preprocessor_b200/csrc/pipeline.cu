@@ -39,6 +39,7 @@ struct CountMirrors {
 __global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t last, int has_vox, int has_stat,
                                   int has_rad, int has_ground, const ApcCtrl* ctrl, uint32_t* out,
                                   const __grid_constant__ CountMirrors mir) {
+  pdl_enter();
   uint32_t c[8];
   c[APC_CNT_INPUT] = n_input;
   c[APC_CNT_FILTERED] = dc[DC_FILTERED];
@@ -205,7 +206,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     k_iota<<<min(apc_div_up(n_total, 256), (uint32_t)APC_SM_COUNT * 4), 256, 0, s>>>(want_row, n_total, dc + cur_cnt);
     APC_LAUNCH_CHECK(ctx, "k_iota");
   }
-  k_pipeline_counts<<<1, 1, 0, s>>>(dc, n_total, cur_cnt, has_vox, has_stat, has_rad, has_ground, ctx->ctrl, out_counts_dev, cmir);
+  apc_klaunch(ctx, k_pipeline_counts, 1, 1, 0, s, dc, n_total, cur_cnt, (int)has_vox, (int)has_stat, (int)has_rad, (int)has_ground, ctx->ctrl,
+              out_counts_dev, cmir);
   APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
   return APC_OK;
 }

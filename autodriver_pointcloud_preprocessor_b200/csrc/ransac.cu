@@ -195,6 +195,7 @@ k_rs_hypotheses(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* 
                 uint64_t seed, const int32_t* __restrict__ table, double* __restrict__ planes) {
   __shared__ uint32_t s_idx[RS_HYP_THREADS][RS_MAX_N + 1];   // +1: rows on different banks
   __shared__ float4 s_sp[RS_HYP_THREADS][RS_MAX_N];
+  pdl_enter();
   const uint32_t P = apc_count(n_dev, n_max);
   const uint32_t tid = threadIdx.x;
   const uint32_t it = blockIdx.x * RS_HYP_THREADS + tid;
@@ -237,6 +238,7 @@ k_rs_score(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   __shared__ float s_hm;                            // hypothesis part of the float32 error bound (chunk max)
   __shared__ float4 s_q[RS_QCAP];                   // points waiting for the exact float64 decision
   __shared__ uint32_t s_qn;
+  pdl_enter();
   const uint32_t P = apc_count(n_dev, n_max);
   const uint32_t h0 = blockIdx.y * CH;
   const uint32_t nh = min((uint32_t)CH, iters - h0);
@@ -536,6 +538,7 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   __shared__ double s_red[8][10];
   __shared__ bool s_last;
   __shared__ uint32_t sm_scan[34];
+  pdl_enter();
   const uint32_t P = apc_count(n_dev, n_max);
   APC_STAMP(1, 0);
   const bool have = info[0] != 0xffffffffu;
@@ -683,13 +686,13 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   const double log1mp = prob < 1.0 ? log(1.0 - prob) : -INFINITY;
   {
     APC_PROF(ctx, "k_rs_hypotheses", s);
-    k_rs_hypotheses<<<apc_div_up(iters, RS_HYP_THREADS), RS_HYP_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, seed, table,
+    apc_klaunch(ctx, k_rs_hypotheses, apc_div_up(iters, RS_HYP_THREADS), RS_HYP_THREADS, 0, s, pts, n_max, n_dev, ransac_n, iters, seed, table,
                                                                               ctx->rs_planes);
   }
   {
     APC_PROF(ctx, "k_rs_score", s);
 #define RS_LAUNCH(CHV)                                                                                              \
-  k_rs_score<CHV><<<grid, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr, ctx->rs_scores, \
+  apc_klaunch(ctx, k_rs_score<CHV>, grid, APC_TILE_THREADS, 0, s, pts, n_max, n_dev, ransac_n, iters, ctx->rs_planes, thr, ctx->rs_scores, \
                                                     log1mp, out_plane, out_info, ctx->rs_scores_copy, ctx->ctrl)
     if (ch == 20) RS_LAUNCH(20);
     else if (ch == 16) RS_LAUNCH(16);
@@ -698,7 +701,7 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
 #undef RS_LAUNCH
   }
   APC_PROF(ctx, "k_rs_final", s);
-  k_rs_final<<<n_tiles, APC_TILE_THREADS, 0, s>>>(pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials,
+  apc_klaunch(ctx, k_rs_final, n_tiles, APC_TILE_THREADS, 0, s, pts, n_max, n_dev, out_plane, out_info, thr, out_mask, ctx->rs_partials,
                                                   reinterpret_cast<float4*>(out_keep_xyzi), out_keep_count,
                                                   ctx->scan_state[scan_slot], n_tiles, ctx->ctrl, keep_idx_in, keep_idx_out,
                                                   mir && out_keep_xyzi ? *mir : MirrorDev{}, nrm_in,

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256)
 k_voxel_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, float vs,
                VoxSlot* __restrict__ slots, VoxAcc* __restrict__ accs, uint32_t cap_mask, uint32_t* __restrict__ p2slot,
                ApcCtrl* ctrl) {
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t stride = gridDim.x * blockDim.x * ITEMS;
   APC_STAMP(0, 0);
@@ -138,6 +139,7 @@ k_voxel_finalize(const float4* __restrict__ pts, uint32_t n_max, const uint32_t*
                  float4* __restrict__ out, uint32_t* __restrict__ out_counts, uint32_t* out_count,
                  uint64_t* scan_state, ApcCtrl* ctrl, uint32_t n_tiles, const __grid_constant__ GridDev grid) {
   __shared__ uint32_t sm_scan[34];
+  pdl_enter();
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t epoch = ctrl->epoch;
   const uint32_t tile = blockIdx.x;
@@ -260,11 +262,11 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
     static const int items = []() { const char* e = getenv("APC_VOX_ITEMS"); return e ? atoi(e) : 1; }();
     if (items >= 4) {
       const uint32_t ib = min(apc_div_up(n_max, 1024), (uint32_t)APC_SM_COUNT * 8);
-      k_voxel_insert<4><<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
+      apc_klaunch(ctx, k_voxel_insert<4>, ib, 256, 0, s, reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
                                            ctx->vox_acc, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
     } else {
       const uint32_t ib = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 8);
-      k_voxel_insert<1><<<ib, 256, 0, s>>>(reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
+      apc_klaunch(ctx, k_voxel_insert<1>, ib, 256, 0, s, reinterpret_cast<const float4*>(xyzi), n_max, n_dev, voxel_size, ctx->vox_slots,
                                            ctx->vox_acc, ctx->hash_cap - 1, ctx->p2slot, ctx->ctrl);
     }
   }
@@ -272,12 +274,12 @@ int apc_voxel_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const uin
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_PROF(ctx, "k_voxel_finalize", s);
   if (radius_grid)
-    k_voxel_finalize<true><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
+    apc_klaunch(ctx, k_voxel_finalize<true>, n_tiles, APC_TILE_THREADS, 0, s,
         reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_acc, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, *radius_grid);
   else
-    k_voxel_finalize<false><<<n_tiles, APC_TILE_THREADS, 0, s>>>(
+    apc_klaunch(ctx, k_voxel_finalize<false>, n_tiles, APC_TILE_THREADS, 0, s,
         reinterpret_cast<const float4*>(xyzi), n_max, n_dev, ctx->p2slot, ctx->vox_slots, ctx->vox_acc, out_p2v ? ctx->vox_rank : nullptr,
         reinterpret_cast<float4*>(out_xyzi), out_voxel_counts, out_count_dev, ctx->scan_state[scan_slot], ctx->ctrl,
         n_tiles, GridDev{});

@@ -131,6 +131,11 @@ class Context:
     def _ok(self, rc):
         _capi.check(self.h, rc)
 
+    def set_low_latency(self, on: bool = True):
+        """One scan in flight at a time: launch the per-scan kernels as programmatic dependents
+        (``apc_ctx_set_low_latency``)."""
+        self._ok(lib.apc_ctx_set_low_latency(self.h, int(bool(on))))
+
     def check(self):
         """Synchronise and raise on data-dependent device errors (key range / capacity)."""
         self._ok(lib.apc_check(self.h, _stream()))

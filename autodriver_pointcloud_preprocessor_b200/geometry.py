@@ -194,6 +194,7 @@ def get_context(n_points: int, device_index: int | None = None) -> engine.Contex
         if ctx is not None:
             ctx.close()
         ctx = engine.Context(max_points=min(cap, MAX_CONTEXT_POINTS), device=idx)
+        ctx.set_low_latency(True)          # the node and the utils functions run one call at a time (pp.py:1056)
         _CONTEXTS[idx] = ctx
     return ctx
 

@@ -117,10 +117,12 @@ class ScanPipeline:
     Parameters mirror the node's (``pointcloud_preprocessor.PointcloudPreprocessorNode``):
     ``fields`` / ``point_step`` / ``n_points`` describe the PointCloud2 layout, ``filter_kw``
     is passed to :func:`engine.make_filter_cfg`, ``stages`` to :func:`engine.make_pipeline_cfg`.
+    ``low_latency``: for ``lanes=1`` (a node processing one scan at a time) - the kernels of a scan
+    are launched as programmatic dependents (``apc_ctx_set_low_latency``).
     """
 
     def __init__(self, fields, point_step: int, n_points: int, filter_kw: dict, stages: dict,
-                 lanes: int = 4, device: int | None = None):
+                 lanes: int = 4, device: int | None = None, low_latency: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA device required: this package has no CPU path")
         self.device_index = torch.cuda.current_device() if device is None else int(device)
@@ -134,6 +136,8 @@ class ScanPipeline:
             ln = _Lane()
             ln.stream = torch.cuda.Stream(device=self.device)
             ln.ctx = engine.Context(max_points=self.n_points, device=self.device_index)
+            if low_latency:                     # one scan in flight per lane: programmatic dependent launches
+                ln.ctx.set_low_latency(True)
             ln.d_in = torch.zeros(self.frame_bytes, dtype=torch.uint8, device=self.device)
             ln.d_out = torch.zeros((self.n_points, 4), dtype=torch.float32, device=self.device)
             ln.d_counts = torch.zeros(8, dtype=torch.int32, device=self.device)

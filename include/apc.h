@@ -120,6 +120,12 @@ const char* apc_last_error(const apc_ctx* ctx);
  * the calls issued since the previous check: APC_OK / APC_ERR_KEY_RANGE / APC_ERR_CAPACITY. */
 int apc_check(apc_ctx* ctx, void* stream);
 int apc_version(void);
+/* Low-latency mode for a context that has ONE scan in flight at a time (the reference's callback model,
+ * pp.py:1056): the kernels of the per-scan chain are launched as programmatic dependents, so every kernel
+ * is set up while its predecessor still runs and starts the moment that one has completed.  Shortens a
+ * scan's latency by the launch gaps between its ~13 kernels; leave it off when several contexts share the
+ * GPU for throughput (the waiting CTAs take room).  Affects launches and graphs captured afterwards. */
+int apc_ctx_set_low_latency(apc_ctx* ctx, int on);
 uint32_t apc_ctx_max_points(const apc_ctx* ctx);
 
 /* Per-kernel timing, the device-side counterpart of the reference's processing_times dict

@@ -229,3 +229,40 @@ def test_concat_eight_sensors_at_the_cloud_limit(big):
     # a ninth sensor is refused
     with pytest.raises(capi.ApcError):
         ctx.frontend(descs + [descs[0]], fcfg, want_src=False)
+
+
+def test_low_latency_mode_is_bit_identical(big):
+    """apc_ctx_set_low_latency (programmatic dependent launches): same counters, rows and plane as the
+    ordinary launches, eager and as a replayed graph, C2 size, five replays."""
+    import bench
+    from autodriver_pointcloud_preprocessor_b200 import engine as eng
+    capi = big["capi"]
+    msg = bench.make_frames(1, seed0=91)[0]
+    data = dev_bytes(msg)
+    fcfg = eng.make_filter_cfg(skip_nans=True, dedup_mode=capi.DEDUP_OPEN3D, remove_nan=True, remove_inf=True,
+                               transforms=[bench.TF], crop=bench.CROP)
+    pcfg = eng.make_pipeline_cfg(fcfg, **bench.STAGES)
+    res = {}
+    for mode in (False, True):
+        ctx = eng.Context(max_points=msg.width)
+        ctx.set_low_latency(mode)
+        desc = eng.make_cloud_desc(msg.fields, msg.point_step, msg.width, data)
+        out, counts, plane = ctx.pipeline_run([desc], pcfg)
+        ctx.check()
+        c = counts.cpu().numpy().copy()
+        n = int(c[capi.CNT_OUTPUT])
+        res[mode] = (c, out[:n].cpu().numpy().copy(), plane.cpu().numpy().copy())
+        o2 = torch.zeros_like(out)
+        c2 = torch.zeros_like(counts)
+        p2 = torch.zeros_like(plane)
+        g = ctx.capture_pipeline([desc], pcfg, o2, c2, p2)
+        for _ in range(5):
+            o2.zero_()
+            ctx.launch_graph(g)
+            ctx.check()
+            assert np.array_equal(c2.cpu().numpy(), c)
+            assert np.array_equal(o2[:n].cpu().numpy().view(np.uint32), res[mode][1].view(np.uint32))
+        ctx.close()
+    assert np.array_equal(res[False][0], res[True][0])
+    assert np.array_equal(res[False][1].view(np.uint32), res[True][1].view(np.uint32))
+    assert np.array_equal(res[False][2], res[True][2])
