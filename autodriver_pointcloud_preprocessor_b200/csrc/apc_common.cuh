@@ -93,6 +93,11 @@ struct apc_ctx {
   float* nrm_scratch = nullptr;     // [3 * max_points] normals of the cloud entering the ground stage (pipeline), on first use
   struct NeighborScratch* neighbors = nullptr;   // neighbour grids + KNN scratch (neighbors.cu), on first use
   bool low_latency = false;         // apc_ctx_set_low_latency: programmatic dependent launches on the pipeline path
+  // profiling probe (APC_LAUNCH_BUDGET=k at context creation, profiles/kernel_marginal.py): only the first k
+  // kernels of every public call are launched, so that the cost of the k-th kernel with all lanes busy is
+  // the difference between two runs.  -1 = off.
+  int launch_budget = -1;
+  mutable int launch_seq = 0;       // launches issued since apc_begin
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.
@@ -157,6 +162,7 @@ static inline uint32_t apc_div_up(uint32_t a, uint32_t b) { return (a + b - 1) /
 template <typename... P, typename... A>
 static inline void apc_klaunch(const apc_ctx* ctx, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
                                cudaStream_t s, A&&... args) {
+  if (ctx->launch_budget >= 0 && ctx->launch_seq++ >= ctx->launch_budget) return;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -46,6 +46,7 @@ int apc_begin(apc_ctx* ctx, cudaStream_t s) {
   int cur = -1;
   if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device)
     return apc_set_error(ctx, APC_ERR_BAD_ARG, "the context lives on another device than the calling thread's current one");
+  ctx->launch_seq = 0;
   apc_klaunch(ctx, k_begin, 1, 32, 0, s, ctx->ctrl);
   APC_LAUNCH_CHECK(ctx, "k_begin");
   return APC_OK;
@@ -98,6 +99,7 @@ extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   apc_ctx* ctx = new apc_ctx();
   ctx->device = device;
   ctx->max_points = max_points;
+  if (const char* lb = getenv("APC_LAUNCH_BUDGET")) ctx->launch_budget = atoi(lb);
   const size_t M = max_points;
   // load factor <= 0.25: short probe chains (the warp-wide worst chain sets the latency).
   // APC_HASH_SLOTS_PER_POINT overrides for experiments.

@@ -254,6 +254,131 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
   APC_STAMP(0, 1);
 }
 
+// ---- radius query over cells of 2r: own cell, then only the neighbours the r-ball can reach ------
+// With a cell edge of 2r (+ slack) the ball around q reaches, along every axis, at most ONE of the two
+// neighbouring cells (the one behind the nearer face), so 1 + 7 cells cover it instead of 27, and a
+// neighbour (a face, edge or corner cell) is visited only if the ball reaches its box: sum over the
+// offset axes of gap^2 <= r^2, gap = distance from q to that face.  On a voxelised 128-beam scan the
+// own cell alone settles 95 % of the keep / drop decisions (cells of r: 75 %), and the others probe
+// 3 to 7 cells, not 26 (profiles/r2p_radius_ab.json).  The set of points tested against d2 <= r2 is a
+// superset of the ball either way, so counts and decisions are bit-identical to the 27-cell walk.
+// Slack: a point of the cell below has x < ix*c exactly, one of the cell above x >= (ix+1)*c*(1 - 2^-24)
+// (grid_coord rounds x/c to nearest); the products, differences and d2 below each carry a relative
+// rounding error of 2^-24.  gap is therefore shortened by 1e-6 * (|q| + c) + 1e-5 * r (8x the worst
+// case); if that ever leaves BOTH faces of an axis within reach (coordinates of tens of kilometres) the
+// query falls back to the 27-cell walk.
+__device__ __forceinline__ uint32_t radius_scan_run(const GridDev& g, uint32_t b, uint32_t f, float4 q, float r2,
+                                                    uint32_t nb_points, int need_counts, uint32_t cnt) {
+  const uint32_t e = b + f;
+  // four points per round: their loads are independent, the exit test runs once per round
+  for (uint32_t t = b; t < e && (need_counts || cnt < nb_points); t += 4) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = g.sorted[min(t + u, e - 1)];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      cnt += (t + u < e && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
+  }
+  return cnt;
+}
+
+// `self` = position of q itself in the cell-sorted array (q = g.sorted[self]).  The own cell is scanned
+// OUTWARDS from that position, two records on either side per round: arrival order inside a cell follows
+// the order of the input (LiDAR firing order), so the records next to q are its neighbours along the scan
+// line and nb_points within r are usually found in the first round or two - scanning the cell from its
+// start examined 14 records per query on the 128-beam scan, this examines 5 to 8.
+__device__ __forceinline__ uint32_t radius_count_oct(const GridDev& g, float c, float4 q, uint32_t self, float r, float r2,
+                                                     uint32_t nb_points, int need_counts) {
+  int32_t ix, iy, iz;
+  grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+  uint32_t cnt = 0, b, f;
+  if (grid_lookup(g, grid_key(0, ix, iy, iz), b, f)) {
+    if (need_counts || self < b || self >= b + f) {
+      cnt = radius_scan_run(g, b, f, q, r2, nb_points, need_counts, 0u);
+    } else {
+      const uint32_t e = b + f;
+      cnt = 1u;                                   // q itself
+      uint32_t up = self + 1, down = self;        // next record above, one past the next record below
+      while (cnt < nb_points && (up < e || down > b)) {
+        float4 p[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          ok[u] = up + u < e;
+          p[u] = g.sorted[ok[u] ? up + u : self];
+          ok[2 + u] = down >= b + 1 + u;
+          p[2 + u] = g.sorted[ok[2 + u] ? down - 1 - u : self];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt += (ok[u] && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
+        up = min(up + 2, e);
+        down = down >= b + 2 ? down - 2 : b;
+      }
+    }
+  }
+  if (!need_counts && cnt >= nb_points) return cnt;
+  const float reach = r * 1.00001f;
+  const float qa[3] = {q.x, q.y, q.z};
+  const int32_t ia[3] = {ix, iy, iz};
+  int32_t dir[3];
+  float gap2[3];
+  bool both = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = __fmul_rn((float)ia[a], c), hi = __fmul_rn((float)(ia[a] + 1), c);
+    const float slack = 1e-6f * (fabsf(qa[a]) + c) + 1e-5f * r;
+    const float gl = fmaxf(0.0f, __fsub_rn(__fsub_rn(qa[a], lo), slack)), gh = fmaxf(0.0f, __fsub_rn(__fsub_rn(hi, qa[a]), slack));
+    dir[a] = gl <= gh ? -1 : 1;
+    const float gmin = fminf(gl, gh);
+    gap2[a] = __fmul_rn(gmin, gmin);
+    both |= fmaxf(gl, gh) <= reach;
+  }
+  if (both) return radius_count(g, c, q, r2, nb_points, need_counts, 27);
+  const float reach2 = __fmul_rn(reach, reach);
+  // faces, edges, corner: the nearer a box, the likelier it holds the missing neighbours.  One cell at a
+  // time: probing the cells of a round together (7 table round trips -> 2) was slower, alone and with all
+  // lanes busy (23.5 vs 22.4 us, 65.1 vs 63.8 us/scan) - most walks end at the first or second face.
+#pragma unroll 1
+  for (int m = 1; m < 8; ++m) {
+    const int mask = (0x7653421 >> (4 * (m - 1))) & 7;     // 1, 2, 4, 3, 5, 6, 7
+    if (!need_counts && cnt >= nb_points) break;
+    const float s2 = ((mask & 1) ? gap2[0] : 0.0f) + ((mask & 2) ? gap2[1] : 0.0f) + ((mask & 4) ? gap2[2] : 0.0f);
+    if (s2 > reach2) continue;
+    const uint64_t key = grid_key(0, ix + ((mask & 1) ? dir[0] : 0), iy + ((mask & 2) ? dir[1] : 0), iz + ((mask & 4) ? dir[2] : 0));
+    if (grid_lookup(g, key, b, f)) cnt = radius_scan_run(g, b, f, q, r2, nb_points, need_counts, cnt);
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+k_radius_query_oct(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r, float r2, uint32_t nb_points, int need_counts,
+                   uint8_t* __restrict__ mask, uint32_t* __restrict__ counts, const ApcCtrl* __restrict__ ctrl) {
+  pdl_enter();
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
+  const float c = grid_cell_size(g, 0);
+  APC_STAMP(0, 0);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float4 q = g.sorted[j];
+    const uint32_t orig = __float_as_uint(q.w);
+    const uint32_t cnt = radius_count_oct(g, c, q, j, r, r2, nb_points, need_counts);
+    mask[orig] = cnt >= nb_points ? 1 : 0;
+    if (counts) counts[orig] = cnt;
+  }
+  APC_STAMP(0, 1);
+}
+
+// Cell edge of the radius grid in units of r (+ 2^-10 slack so that d2 <= r2 never reaches past the
+// neighbouring cell): >= 2 = the pruned 8-cell walk above (default 2), 1 = the 27-cell walk (APC_RADIUS_CELL).
+static float radius_cell_mult() {
+  static const float m = []() {
+    const char* e = getenv("APC_RADIUS_CELL");
+    const float v = e ? (float)atof(e) : 2.0f;
+    return v >= 2.0f ? v : 1.0f;
+  }();
+  return m;
+}
+static float radius_cell(float r32) { return r32 * radius_cell_mult() * 1.0009765625f; }
+
 // The keep / drop decision in two launches (the exact counts are not wanted):
 //   fast  every point against its OWN cell only - one probe, one or two rounds of loads, every thread
 //         done within the same few microseconds; the few that did not reach nb_points there are
@@ -301,10 +426,16 @@ k_radius_slow(GridDev g, float r2, uint32_t nb_points, uint8_t* __restrict__ mas
 }
 
 // decision-only radius query: the single launch (default) or the split (APC_RADIUS_SPLIT=1)
-static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const uint32_t* n_dev, float r2, uint32_t nb_points,
-                         uint8_t* mask, cudaStream_t s) {
+static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const uint32_t* n_dev, float r, float r2,
+                         uint32_t nb_points, uint8_t* mask, cudaStream_t s) {
   static const bool split = []() { const char* e = getenv("APC_RADIUS_SPLIT"); return e && atoi(e) != 0; }();
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
+  if (radius_cell_mult() >= 2.0f) {
+    APC_PROF(ctx, "k_radius_query", s);
+    apc_klaunch(ctx, k_radius_query_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    APC_LAUNCH_CHECK(ctx, "k_radius_query_oct");
+    return APC_OK;
+  }
   if (!split) {
     APC_PROF(ctx, "k_radius_query", s);
     apc_klaunch(ctx, k_radius_query, bq, 128, 0, s, n_max, n_dev, g, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
@@ -779,16 +910,19 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   // cells of r (+ slack, so that d2 <= r2 never reaches 2 cells away); measured alternatives at
   // 200k points: cells of 2r 37 us, one warp per cell group with shuffled broadcasts 85 us,
   // neighbour-cell lookups issued in rounds of 6-13 32-50 us, this per-thread walk 29-32 us
-  const float cell = r32 * 1.0009765625f;
+  const float cell = radius_cell(r32);
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
   rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
   if (rc) return rc;
   if (out_counts) {
     const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
     APC_PROF(ctx, "k_radius_query", s);
-    apc_klaunch(ctx, k_radius_query, bq, 128, 0, s, n_max, n_dev, g.d, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
+    if (radius_cell_mult() >= 2.0f)
+      apc_klaunch(ctx, k_radius_query_oct, bq, 128, 0, s, n_max, n_dev, g.d, r32, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
+    else
+      apc_klaunch(ctx, k_radius_query, bq, 128, 0, s, n_max, n_dev, g.d, r2, (uint32_t)nb_points, 1, out_mask, out_counts, ctx->ctrl);
   } else {
-    rc = radius_decide(ctx, g.d, n_max, n_dev, r2, (uint32_t)nb_points, out_mask, s);
+    rc = radius_decide(ctx, g.d, n_max, n_dev, r32, r2, (uint32_t)nb_points, out_mask, s);
     if (rc) return rc;
   }
   const dim3 grid(min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4), 1);
@@ -849,7 +983,7 @@ int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
   int rc = apc_neighbors_prepare(ctx, 0);
   if (rc) return rc;
   GridHost& g = scratch_of(ctx)->grid[0];
-  g.d.cell0 = (float)radius * 1.0009765625f;
+  g.d.cell0 = radius_cell((float)radius);
   *out = g.d;
   return APC_OK;
 }
@@ -871,9 +1005,9 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   GridHost& g = scratch_of(ctx)->grid[0];
   const float r32 = (float)radius;
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
-  rc = grid_build(ctx, g, pts, n_max, n_dev, r32 * 1.0009765625f, false, s, points_inserted != 0);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, radius_cell(r32), false, s, points_inserted != 0);
   if (rc) return rc;
-  rc = radius_decide(ctx, g.d, n_max, n_dev, r32 * r32, (uint32_t)nb_points, mask_scratch, s);
+  rc = radius_decide(ctx, g.d, n_max, n_dev, r32, r32 * r32, (uint32_t)nb_points, mask_scratch, s);
   if (rc) return rc;
   const uint32_t n_tiles = apc_div_up(n_max, APC_TILE_POINTS);
   APC_REQUIRE(ctx, n_tiles <= ctx->max_tiles, "more points than the context was created for");

@@ -46,10 +46,12 @@ with torch.cuda.stream(ln.stream):
 tot = sum(v[0] / v[1] for v in prof.values())
 print(f"graph p50 {np.median(lat):.1f} us   sum of kernels {tot * 1e3:.1f} us   kernels/scan {pipe.kernels_per_scan}")
 counts = ln.d_counts.cpu().numpy().astype(float)
-cnt = {"N": counts[_capi.CNT_INPUT], "M": counts[_capi.CNT_FILTERED], "V": counts[_capi.CNT_VOXELS],
-       "P_radius_in": counts[_capi.CNT_VOXELS], "P_ground_in": counts[_capi.CNT_AFTER_RADIUS], "out": counts[_capi.CNT_OUTPUT]}
+cnt = {"N": counts[_capi.CNT_INPUT], "ps": float(bench.POINT_STEP), "M": counts[_capi.CNT_FILTERED], "V": counts[_capi.CNT_VOXELS],
+       "Ps": counts[_capi.CNT_AFTER_STAT], "Pr": counts[_capi.CNT_AFTER_RADIUS], "K": counts[_capi.CNT_GROUND_INLIERS],
+       "O": counts[_capi.CNT_OUTPUT]}
 print(f"points per scan {bench.N_POINTS}: " + ", ".join(f"{k}={int(v)}" for k, v in cnt.items()))
 for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-    ab = bench.algorithmic_bytes(k, cnt)
+    kb = bench.kernel_bytes(k, cnt)
+    ab = kb[0] if kb else None
     gbs = f"{ab / (ms / n * 1e-3) / 1e9:8.1f} GB/s algorithmic" if ab else ""
     print(f"  {k:22s} {ms / n * 1e3:8.2f} us {gbs}")
