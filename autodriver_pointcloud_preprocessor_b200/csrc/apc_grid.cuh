@@ -23,6 +23,7 @@ struct GridDev {
   float4* sorted;            // [levels][n_max] xyz + original index (bits in w)
   float* cell;               // [levels] cell sizes (device)
   float cell0;               // > 0: single-level grid whose cell size the host knows (no k_grid_cells launch)
+  float inv0;                // > 0: cell index = floor(x * inv0) instead of floor(x / cell0) (see grid_coord_g)
   uint32_t cursor_base;      // first ctrl->counters slot of this grid's per-level scatter cursors (the radius
                              // grid and the KNN grid can both be built inside one pipeline run)
 };
@@ -33,6 +34,21 @@ __device__ __forceinline__ float grid_cell_size(const GridDev& g, uint32_t level
 __device__ __forceinline__ bool grid_coord(float x, float y, float z, float c, int32_t& ix, int32_t& iy, int32_t& iz) {
   const float qx = floorf(__fdiv_rn(x, c)), qy = floorf(__fdiv_rn(y, c)), qz = floorf(__fdiv_rn(z, c));
   const float h = 262143.0f;  // one cell of margin for the +-1 neighbour offsets
+  if (!(qx >= -h && qx < h && qy >= -h && qy < h && qz >= -h && qz < h)) return false;
+  ix = (int32_t)qx; iy = (int32_t)qy; iz = (int32_t)qz;
+  return true;
+}
+// Cell of a point in grid g.  The index only has to be the SAME function at insert and at query time and
+// to respect the walk's slack; for the radius grid (cells of 2r, box-pruned walk with an explicit slack of
+// 8 float32 ulps of the coordinate, neighbors.cu) the three IEEE divisions by the cell size - a quarter of
+// the instructions of the kernel that inserts the centroids - are one multiplication each by the
+// host-rounded reciprocal.  Every other grid (27-cell walks whose guarantee is the 2^-10 margin on the
+// cell size) keeps the division.
+__device__ __forceinline__ bool grid_coord_g(const GridDev& g, float c, float x, float y, float z, int32_t& ix, int32_t& iy,
+                                             int32_t& iz) {
+  if (!(g.inv0 > 0.0f)) return grid_coord(x, y, z, c, ix, iy, iz);
+  const float qx = floorf(__fmul_rn(x, g.inv0)), qy = floorf(__fmul_rn(y, g.inv0)), qz = floorf(__fmul_rn(z, g.inv0));
+  const float h = 262143.0f;
   if (!(qx >= -h && qx < h && qy >= -h && qy < h && qz >= -h && qz < h)) return false;
   ix = (int32_t)qx; iy = (int32_t)qy; iz = (int32_t)qz;
   return true;
@@ -48,7 +64,7 @@ __device__ __forceinline__ void grid_insert_point(const GridDev& g, uint32_t lev
   int32_t ix, iy, iz;
   slot = GRID_NOSLOT;
   rank = 0;
-  if (!grid_coord(x, y, z, c, ix, iy, iz)) {
+  if (!grid_coord_g(g, c, x, y, z, ix, iy, iz)) {
     atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
     return;
   }
@@ -76,7 +92,7 @@ __device__ __forceinline__ void grid_insert_items(const GridDev& g, uint32_t lev
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     int32_t ix = 0, iy = 0, iz = 0;
-    go[j] = act[j] && grid_coord(p[j].x, p[j].y, p[j].z, c, ix, iy, iz);
+    go[j] = act[j] && grid_coord_g(g, c, p[j].x, p[j].y, p[j].z, ix, iy, iz);
     if (act[j] && !go[j]) atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
     key[j] = grid_key(level, ix, iy, iz);
     s[j] = (uint32_t)mix64(key[j]) & g.cap_mask;

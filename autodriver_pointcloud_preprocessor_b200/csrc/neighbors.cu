@@ -75,7 +75,7 @@ k_grid_insert(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_
     bool ok = false;
     if (i < n) {
       p = pts[i];
-      ok = grid_coord(p.x, p.y, p.z, c, ix, iy, iz);
+      ok = grid_coord_g(g, c, p.x, p.y, p.z, ix, iy, iz);
       if (!ok) atomicOr(&ctrl->err, APC_DEVERR_KEY_RANGE);
     }
     const uint32_t vm = __ballot_sync(0xffffffffu, ok);
@@ -203,7 +203,7 @@ __device__ __forceinline__ uint32_t grid_sorted_count(const GridDev& g, const Ap
 __device__ __forceinline__ uint32_t radius_count(const GridDev& g, float c, float4 q, float r2, uint32_t nb_points,
                                                  int need_counts, int n_cells) {
   int32_t ix, iy, iz;
-  grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+  grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz);  // succeeded at insert time
   uint32_t cnt = 0;
   // own cell first, then faces, edges, corners: when only the keep/drop decision is wanted
   // most points reach nb_points inside their own cell and stop there.  The first probe of the
@@ -262,9 +262,9 @@ k_radius_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint3
 // own cell alone settles 95 % of the keep / drop decisions (cells of r: 75 %), and the others probe
 // 3 to 7 cells, not 26 (profiles/r2p_radius_ab.json).  The set of points tested against d2 <= r2 is a
 // superset of the ball either way, so counts and decisions are bit-identical to the 27-cell walk.
-// Slack: a point of the cell below has x < ix*c exactly, one of the cell above x >= (ix+1)*c*(1 - 2^-24)
-// (grid_coord rounds x/c to nearest); the products, differences and d2 below each carry a relative
-// rounding error of 2^-24.  gap is therefore shortened by 1e-6 * (|q| + c) + 1e-5 * r (8x the worst
+// Slack: the cell index is floor(fl(x * fl(1/c))) (grid_coord_g), two roundings of 2^-24 each, so a point
+// of the cell below has x < ix*c*(1 + 2^-23) and one of the cell above x >= (ix+1)*c*(1 - 2^-23); the
+// products, differences and d2 below each carry a relative rounding error of 2^-24.  gap is therefore shortened by 1e-6 * (|q| + c) + 1e-5 * r (8x the worst
 // case); if that ever leaves BOTH faces of an axis within reach (coordinates of tens of kilometres) the
 // query falls back to the 27-cell walk.
 __device__ __forceinline__ uint32_t radius_scan_run(const GridDev& g, uint32_t b, uint32_t f, float4 q, float r2,
@@ -290,7 +290,7 @@ __device__ __forceinline__ uint32_t radius_scan_run(const GridDev& g, uint32_t b
 __device__ __forceinline__ uint32_t radius_count_oct(const GridDev& g, float c, float4 q, uint32_t self, float r, float r2,
                                                      uint32_t nb_points, int need_counts) {
   int32_t ix, iy, iz;
-  grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+  grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz);  // succeeded at insert time
   uint32_t cnt = 0, b, f;
   if (grid_lookup(g, grid_key(0, ix, iy, iz), b, f)) {
     if (need_counts || self < b || self >= b + f) {
@@ -508,7 +508,7 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
     for (uint32_t level = 0; level < g.levels && !done; ++level) {
       const float c = g.cell[level];
       int32_t ix, iy, iz;
-      if (!grid_coord(q.x, q.y, q.z, c, ix, iy, iz)) continue;
+      if (!grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz)) continue;
       // 1. the 27 cells, one per lane
       uint32_t cs = 0, cf = 0;
       if (lane < 27) {
@@ -872,7 +872,8 @@ int apc_neighbors_reset(apc_ctx* ctx, cudaStream_t s) {
 }
 
 static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_max, const uint32_t* n_dev,
-                      float cell_hint, bool need_bbox, cudaStream_t s, bool inserted = false, uint32_t cursor_base = 0) {
+                      float cell_hint, bool need_bbox, cudaStream_t s, bool inserted = false, uint32_t cursor_base = 0,
+                      bool reciprocal = false) {
   if (g.d.levels == 1) g.d.cursor_base = cursor_base ? cursor_base : CTR_CURSOR_RADIUS;
   const uint32_t bx = min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT * 4);
   if (need_bbox) {
@@ -880,6 +881,7 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
     k_bbox<<<bx, 256, 0, s>>>(pts, n_max, n_dev, ctx->ctrl);
   }
   g.d.cell0 = (g.d.levels == 1 && cell_hint > 0.0f) ? cell_hint : 0.0f;
+  g.d.inv0 = (reciprocal && g.d.cell0 > 0.0f) ? 1.0f / g.d.cell0 : 0.0f;
   if (!(g.d.cell0 > 0.0f)) k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
   const dim3 grid(bx, g.d.levels);
   if (!inserted) {   // (the pipeline's voxel stage inserts its centroids as it writes them)
@@ -912,7 +914,7 @@ int apc_radius_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, const ui
   // neighbour-cell lookups issued in rounds of 6-13 32-50 us, this per-thread walk 29-32 us
   const float cell = radius_cell(r32);
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
-  rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, cell, false, s, false, 0, radius_cell_mult() >= 2.0f);
   if (rc) return rc;
   if (out_counts) {
     const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
@@ -984,6 +986,7 @@ int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
   if (rc) return rc;
   GridHost& g = scratch_of(ctx)->grid[0];
   g.d.cell0 = radius_cell((float)radius);
+  g.d.inv0 = radius_cell_mult() >= 2.0f ? 1.0f / g.d.cell0 : 0.0f;
   *out = g.d;
   return APC_OK;
 }
@@ -1005,7 +1008,7 @@ int apc_radius_select_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
   GridHost& g = scratch_of(ctx)->grid[0];
   const float r32 = (float)radius;
   const float4* pts = reinterpret_cast<const float4*>(xyzi);
-  rc = grid_build(ctx, g, pts, n_max, n_dev, radius_cell(r32), false, s, points_inserted != 0);
+  rc = grid_build(ctx, g, pts, n_max, n_dev, radius_cell(r32), false, s, points_inserted != 0, 0, radius_cell_mult() >= 2.0f);
   if (rc) return rc;
   rc = radius_decide(ctx, g.d, n_max, n_dev, r32, r32 * r32, (uint32_t)nb_points, mask_scratch, s);
   if (rc) return rc;
@@ -1237,7 +1240,7 @@ k_normals_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
     int32_t ix, iy, iz;
-    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+    grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz);  // succeeded at insert time
     NearList nl;
     nl.cnt = 0;
     nl.worst = 0;
@@ -1298,7 +1301,7 @@ k_normals_cov(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
     int32_t ix, iy, iz;
-    grid_coord(q.x, q.y, q.z, c, ix, iy, iz);  // succeeded at insert time
+    grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz);  // succeeded at insert time
     uint32_t cs = 0, cf = 0;
     if (lane < 27) {
       const int dx = (int)(lane % 3u) - 1, dy = (int)((lane / 3u) % 3u) - 1, dz = (int)(lane / 9u) - 1;

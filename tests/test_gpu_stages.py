@@ -276,6 +276,29 @@ def test_radius_outliers_parity(env):
     assert np.array_equal(mask.cpu().numpy(), mask2.cpu().numpy())
 
 
+@pytest.mark.parametrize("centre", [(0.0, 0.0, 0.0), (30000.0, -20000.0, 5.0), (-65000.0, 65000.0, -100.0)])
+def test_radius_query_box_pruning_is_exact(env, centre):
+    """Cells of 2r with box-pruned neighbour cells (k_radius_query_oct): exact counts and keep / drop
+    decisions equal the exhaustive float32 count for a dense random blob - every face / edge / corner case
+    of the pruning - also tens of kilometres from the origin, where a float32 ulp of the coordinates
+    (4 mm at 65 km) approaches the pruning slack and the query falls back to the 27-cell walk."""
+    from oracle import outliers
+    ctx = env["ctx"]
+    rng = np.random.default_rng(17)
+    pts = np.zeros((4000, 4), dtype=np.float32)
+    pts[:, :3] = (np.asarray(centre) + rng.uniform(-2.0, 2.0, size=(4000, 3))).astype(np.float32)
+    dev = torch.from_numpy(pts).cuda()
+    for nb, r in ((5, 0.5), (9, 0.35), (40, 1.0)):
+        ref = outliers.radius_counts_brute(pts[:, :3], r)
+        mask, counts = ctx.radius_outliers(dev, nb, r, want_counts=True)
+        ctx.check()
+        assert np.array_equal(counts.cpu().numpy().astype(np.uint32), ref)
+        mask2, _ = ctx.radius_outliers(dev, nb, r, want_counts=False)         # early exit, scan outwards from the query
+        ctx.check()
+        assert np.array_equal(mask2.cpu().numpy().astype(bool), ref >= nb)
+        assert np.array_equal(mask.cpu().numpy(), mask2.cpu().numpy())
+
+
 def test_statistical_outliers_parity(env):
     from oracle import outliers
     ctx = env["ctx"]
