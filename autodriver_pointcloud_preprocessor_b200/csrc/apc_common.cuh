@@ -98,6 +98,7 @@ struct apc_ctx {
   // the difference between two runs.  -1 = off.
   int launch_budget = -1;
   mutable int launch_seq = 0;       // launches issued since apc_begin
+  bool fold_begin = false;          // run_pipeline -> apc_frontend_nobegin: k_dedup_insert does k_begin's work (see apc_begin_folded)
 };
 
 // RAII timer around one kernel launch; a no-op unless profiling is enabled on the context.
@@ -131,6 +132,9 @@ struct ProfScope {
 int apc_set_error(apc_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess);
 // bumps the epoch; every public entry point calls it first
 int apc_begin(apc_ctx* ctx, cudaStream_t s);
+// The same without the k_begin launch: the first kernel of the call bumps the epoch and zeroes the counters
+// itself (begin_in_kernel below) - it must neither read them nor run concurrently with a kernel that does.
+int apc_begin_folded(apc_ctx* ctx);
 
 #define APC_CUDA(ctx, call)                                                \
   do {                                                                     \
@@ -187,6 +191,42 @@ __device__ __forceinline__ void pdl_enter() {
 
 // ---- device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// k_begin's work, done by the first 32 threads of one CTA of the call's first kernel
+__device__ __forceinline__ void begin_in_kernel(ApcCtrl* ctrl) {
+  if (threadIdx.x == 0) ctrl->epoch = ctrl->epoch + 1u;
+  if (threadIdx.x < 30) ctrl->counters[threadIdx.x] = 0u;
+}
+
+// The pipeline's eight output counters (APC_CNT_*), assembled from the stages' device counters by the
+// kernel that runs last: the ticket-last CTA of k_rs_final when the pipeline ends with ground removal
+// (one launch less on every scan of the C1 / C2 configurations), else the one-thread k_pipeline_counts.
+struct CountsEpilogue {
+  const uint32_t* dc;          // the context's dev_counts (NULL: no epilogue)
+  uint32_t* out;               // uint32[8]
+  uint32_t n_input, last;
+  int has_vox, has_stat, has_rad, has_ground;
+  uint32_t n_mir;
+  uint32_t* mir[APC_MAX_MIRRORS];   // the peers' copies of this frame's counters (see apc_out_mirror)
+};
+__device__ __forceinline__ void pipeline_counts_write(const CountsEpilogue& e, const ApcCtrl* ctrl) {
+  const volatile uint32_t* dc = e.dc;
+  uint32_t c[8];
+  c[APC_CNT_INPUT] = e.n_input;
+  c[APC_CNT_FILTERED] = dc[1];
+  uint32_t cur = dc[1];
+  c[APC_CNT_VOXELS] = cur = e.has_vox ? dc[2] : cur;
+  c[APC_CNT_AFTER_STAT] = cur = e.has_stat ? dc[3] : cur;
+  c[APC_CNT_AFTER_RADIUS] = cur = e.has_rad ? dc[4] : cur;
+  c[APC_CNT_GROUND_INLIERS] = e.has_ground ? dc[8 + 1] : 0u;
+  c[APC_CNT_OUTPUT] = dc[e.last];
+  c[APC_CNT_STATUS] = *reinterpret_cast<const volatile uint32_t*>(&ctrl->err);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) e.out[k] = c[k];
+  for (uint32_t m = 0; m < e.n_mir; ++m)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e.mir[m][k] = c[k];
+}
 
 __device__ __forceinline__ uint32_t apc_count(const uint32_t* n_dev, uint32_t n_max) {
   uint32_t n = n_dev ? *n_dev : n_max;

@@ -89,6 +89,14 @@ extern "C" int apc_ctx_destroy(apc_ctx* ctx) {
   return APC_OK;
 }
 
+int apc_begin_folded(apc_ctx* ctx) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device)
+    return apc_set_error(ctx, APC_ERR_BAD_ARG, "the context lives on another device than the calling thread's current one");
+  ctx->launch_seq = 0;
+  return APC_OK;
+}
+
 extern "C" int apc_ctx_create(int device, uint32_t max_points, apc_ctx** out) {
   if (!out) return apc_set_error(nullptr, APC_ERR_BAD_ARG, "out is NULL");
   *out = nullptr;

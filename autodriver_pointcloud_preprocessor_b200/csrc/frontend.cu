@@ -34,6 +34,7 @@ struct FrontendParams {
   uint32_t* out_count;
   uint64_t* scan_state;
   ApcCtrl* ctrl;
+  uint32_t do_begin;      // k_dedup_insert is the first kernel of the call: CTA 0 does k_begin's work
 };
 
 // ---- duplicate removal: 64-bit open-addressing slots {fingerprint:32 | lowest point index:32} -----
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_dedup_insert(const __grid_
   __shared__ __align__(8) uint64_t bar;
   pdl_enter();
   const uint32_t tile = blockIdx.x;
+  if (prm.do_begin && tile == 0) begin_in_kernel(prm.ctrl);   // nothing in this kernel reads the epoch or the counters
   const uint32_t si = find_segment(prm, tile);
   const SegDev& s = prm.seg[si];
   TilePoint pt[APC_TILE_ITEMS];
@@ -496,6 +498,8 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
   rc = set_smem(ctx, smem);
   if (rc) return rc;
   const bool generic = smem != 0;   // some segment needs the byte-record decoder
+  APC_REQUIRE(ctx, !ctx->fold_begin || prm.dedup, "folded begin needs the duplicate-insert kernel");
+  prm.do_begin = ctx->fold_begin ? 1u : 0u;
   if (prm.dedup) {
     APC_PROF(ctx, "k_dedup_insert", s);
     if (generic) apc_klaunch(ctx, k_dedup_insert<true>, prm.n_tiles, APC_TILE_THREADS, smem, s, prm);

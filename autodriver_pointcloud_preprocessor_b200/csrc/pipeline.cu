@@ -23,38 +23,18 @@ int apc_statistical_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, i
                             double*, cudaStream_t);
 int apc_segment_plane_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, double, int, int, double, uint64_t,
                               const int32_t*, double*, uint8_t*, uint32_t*, float*, uint32_t*, int, cudaStream_t,
-                              const uint32_t*, uint32_t*, const MirrorDev*, const float*, float*);
+                              const uint32_t*, uint32_t*, const MirrorDev*, const float*, float*, const CountsEpilogue*);
 int apc_normals_nobegin(apc_ctx*, const float*, uint32_t, const uint32_t*, int, double, float*, uint32_t*, double*, cudaStream_t);
 int apc_neighbors_prepare(apc_ctx*, int);
 int apc_normals_prepare(apc_ctx*, int);
 int apc_sort_prepare(apc_ctx*);
 
 // dev_counts layout inside the context
-enum { DC_FILTERED = 1, DC_VOXELS = 2, DC_STAT = 3, DC_RADIUS = 4, DC_OUT = 6, DC_INFO = 8 /* 4 words */ };
+enum { DC_FILTERED = 1, DC_VOXELS = 2, DC_STAT = 3, DC_RADIUS = 4, DC_OUT = 6, DC_INFO = 8 /* 4 words */ };   // pipeline_counts_write reads 1, 2, 3, 4, 8 + 1
 
-struct CountMirrors {
-  uint32_t n;
-  uint32_t* out[APC_MAX_MIRRORS];
-};
-__global__ void k_pipeline_counts(const uint32_t* dc, uint32_t n_input, uint32_t last, int has_vox, int has_stat,
-                                  int has_rad, int has_ground, const ApcCtrl* ctrl, uint32_t* out,
-                                  const __grid_constant__ CountMirrors mir) {
+__global__ void k_pipeline_counts(const __grid_constant__ CountsEpilogue fin, const ApcCtrl* ctrl) {
   pdl_enter();
-  uint32_t c[8];
-  c[APC_CNT_INPUT] = n_input;
-  c[APC_CNT_FILTERED] = dc[DC_FILTERED];
-  uint32_t cur = dc[DC_FILTERED];
-  c[APC_CNT_VOXELS] = cur = has_vox ? dc[DC_VOXELS] : cur;
-  c[APC_CNT_AFTER_STAT] = cur = has_stat ? dc[DC_STAT] : cur;
-  c[APC_CNT_AFTER_RADIUS] = cur = has_rad ? dc[DC_RADIUS] : cur;
-  c[APC_CNT_GROUND_INLIERS] = has_ground ? dc[DC_INFO + 1] : 0u;
-  c[APC_CNT_OUTPUT] = dc[last];
-  c[APC_CNT_STATUS] = ctrl->err;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = c[k];
-  for (uint32_t m = 0; m < mir.n; ++m)      // the peers' copies of this frame's counters (see apc_out_mirror)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mir.out[m][k] = c[k];
+  pipeline_counts_write(fin, ctrl);
   APC_STAMP(0, 0);
 }
 
@@ -74,7 +54,7 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
                         const apc_pipeline_maps* maps = nullptr, const apc_out_mirror* mirror = nullptr) {
   APC_REQUIRE(ctx, clouds && cfg && out_xyzi && out_counts_dev, "NULL pointer");
   MirrorDev mir{};
-  CountMirrors cmir{};
+  CountsEpilogue fin{};
   if (mirror) {
     APC_REQUIRE(ctx, mirror->n_xyzi <= APC_MAX_MIRRORS && mirror->n_counts <= APC_MAX_MIRRORS, "too many mirrors");
     APC_REQUIRE(ctx, mirror->n_xyzi == 0 || cfg->stat_enable || cfg->radius_enable || cfg->ground_enable,
@@ -85,10 +65,10 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
       APC_REQUIRE(ctx, mirror->xyzi_dev[k], "mirror pointer is NULL");
       mir.out[k] = reinterpret_cast<float4*>(mirror->xyzi_dev[k]);
     }
-    cmir.n = mirror->n_counts;
-    for (uint32_t k = 0; k < cmir.n; ++k) {
+    fin.n_mir = mirror->n_counts;
+    for (uint32_t k = 0; k < fin.n_mir; ++k) {
       APC_REQUIRE(ctx, mirror->counts_dev[k], "mirror pointer is NULL");
-      cmir.out[k] = mirror->counts_dev[k];
+      fin.mir[k] = mirror->counts_dev[k];
     }
   }
   uint32_t n_total = 0;
@@ -98,8 +78,12 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   const int n_stages = 1 + has_vox + has_stat + has_rad + has_ground;
   const bool has_normals = cfg->normals_enable != 0;
   APC_REQUIRE(ctx, !has_normals || (maps && maps->normals_dev), "normals_enable needs maps.normals_dev");
-  int rc = apc_begin(ctx, s);
+  // first kernel = k_dedup_insert (it uses neither the epoch nor the counters): it does k_begin's work
+  static const bool fold_env = getenv("APC_NO_FOLD") == nullptr;   // A/B knob for profiles/
+  const bool fold_begin = fold_env && cfg->filter.dedup_mode == APC_DEDUP_OPEN3D && n_total > 0;
+  int rc = fold_begin ? apc_begin_folded(ctx) : apc_begin(ctx, s);
   if (rc) return rc;
+  ctx->fold_begin = fold_begin;
   uint32_t* dc = ctx->dev_counts;
   float* ping = reinterpret_cast<float*>(ctx->buf_a);
   float* pong = reinterpret_cast<float*>(ctx->buf_b);
@@ -117,6 +101,12 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   };
   // index maps (apc_pipeline_run_maps): every selection after the voxel stage also carries, per
   // surviving point, its row in the cloud the voxel stage produced; the last one writes out_row
+  fin.dc = dc;
+  fin.out = out_counts_dev;
+  fin.n_input = n_total;
+  fin.last = DC_OUT;                     // when the ground stage writes the counters it is the last stage
+  fin.has_vox = has_vox; fin.has_stat = has_stat; fin.has_rad = has_rad; fin.has_ground = has_ground;
+  bool counts_done = false;
   uint32_t* const want_row = maps ? maps->out_row_dev : nullptr;
   int sel_left = want_row ? has_stat + has_rad + has_ground : 0;
   const uint32_t* row_in = nullptr;
@@ -130,6 +120,7 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   uint32_t cur_cnt = DC_FILTERED;
   rc = apc_frontend_nobegin(ctx, clouds, n_clouds, &cfg->filter, cur, maps ? maps->src_idx_dev : nullptr, nullptr,
                             dc + DC_FILTERED, 0, s);
+  ctx->fold_begin = false;
   if (rc) return rc;
   static const int n_dummy = []() { const char* e = getenv("APC_DUMMY_KERNELS"); return e ? atoi(e) : 0; }();
   for (int k = 0; k < n_dummy; ++k) k_nop<<<1, 32, 0, s>>>(ctx->ctrl);
@@ -196,7 +187,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     rc = apc_segment_plane_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->ground_distance_threshold, cfg->ground_ransac_n,
                                    cfg->ground_num_iterations, cfg->ground_probability, cfg->ground_seed, nullptr, plane,
                                    nullptr, dc + DC_INFO, out, dc + DC_OUT, 4, s, row_in, rows, last_mir(), nrm_in,
-                                   nrm_in ? maps->normals_dev : nullptr);
+                                   nrm_in ? maps->normals_dev : nullptr, fold_env && n_total ? &fin : nullptr);
+    counts_done = fold_env && n_total;
     if (rc) return rc;
     row_in = rows;
     cur = out;
@@ -206,9 +198,11 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     k_iota<<<min(apc_div_up(n_total, 256), (uint32_t)APC_SM_COUNT * 4), 256, 0, s>>>(want_row, n_total, dc + cur_cnt);
     APC_LAUNCH_CHECK(ctx, "k_iota");
   }
-  apc_klaunch(ctx, k_pipeline_counts, 1, 1, 0, s, dc, n_total, cur_cnt, (int)has_vox, (int)has_stat, (int)has_rad, (int)has_ground, ctx->ctrl,
-              out_counts_dev, cmir);
-  APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
+  if (!counts_done) {
+    fin.last = cur_cnt;
+    apc_klaunch(ctx, k_pipeline_counts, 1, 1, 0, s, fin, ctx->ctrl);
+    APC_LAUNCH_CHECK(ctx, "k_pipeline_counts");
+  }
   return APC_OK;
 }
 

@@ -534,7 +534,8 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
            uint32_t* __restrict__ info, double thr, uint8_t* __restrict__ mask, double* __restrict__ partials,
            float4* __restrict__ keep_out, uint32_t* keep_count, uint64_t* scan_state, uint32_t n_tiles, ApcCtrl* ctrl,
            const uint32_t* __restrict__ keep_idx_in, uint32_t* __restrict__ keep_idx_out,
-           const __grid_constant__ MirrorDev mir, const float* __restrict__ nrm_in, float* __restrict__ nrm_out) {
+           const __grid_constant__ MirrorDev mir, const float* __restrict__ nrm_in, float* __restrict__ nrm_out,
+           const __grid_constant__ CountsEpilogue fin) {
   __shared__ double s_red[8][10];
   __shared__ bool s_last;
   __shared__ uint32_t sm_scan[34];
@@ -630,6 +631,8 @@ k_rs_final(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev
   if (threadIdx.x == 0) {
     const double n = s_tot[0];
     info[1] = (uint32_t)n;
+    // every other CTA has retired its results before its ticket: the stage counters are final
+    if (fin.dc) pipeline_counts_write(fin, ctrl);
     if (n < 1.0) { plane8[0] = plane8[1] = plane8[2] = plane8[3] = 0.0; return; }
     const double cx = s_tot[1] / n, cy = s_tot[2] / n, cz = s_tot[3] / n;
     const double xx = s_tot[4] - n * cx * cx, xy = s_tot[5] - n * cx * cy, xz = s_tot[6] - n * cx * cz;
@@ -643,7 +646,8 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
                               int ransac_n, int iters, double prob, uint64_t seed, const int32_t* table,
                               double* out_plane, uint8_t* out_mask, uint32_t* out_info, float* out_keep_xyzi,
                               uint32_t* out_keep_count, int scan_slot, cudaStream_t s, const uint32_t* keep_idx_in,
-                              uint32_t* keep_idx_out, const MirrorDev* mir, const float* nrm_in, float* nrm_out) {
+                              uint32_t* keep_idx_out, const MirrorDev* mir, const float* nrm_in, float* nrm_out,
+                              const CountsEpilogue* fin) {
   APC_REQUIRE(ctx, out_plane && out_info && (out_mask || out_keep_xyzi), "NULL output pointer");
   APC_REQUIRE(ctx, !out_keep_xyzi || out_keep_count, "out_keep_count is NULL");
   APC_REQUIRE(ctx, prob > 0.0 && prob <= 1.0, "probability must be in (0, 1]");
@@ -705,7 +709,7 @@ int apc_segment_plane_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, c
                                                   reinterpret_cast<float4*>(out_keep_xyzi), out_keep_count,
                                                   ctx->scan_state[scan_slot], n_tiles, ctx->ctrl, keep_idx_in, keep_idx_out,
                                                   mir && out_keep_xyzi ? *mir : MirrorDev{}, nrm_in,
-                                                  out_keep_xyzi ? nrm_out : nullptr);
+                                                  out_keep_xyzi ? nrm_out : nullptr, fin ? *fin : CountsEpilogue{});
   APC_LAUNCH_CHECK(ctx, "segment_plane");
   return APC_OK;
 }
@@ -721,7 +725,7 @@ extern "C" int apc_segment_plane(apc_ctx* ctx, const float* xyzi, uint32_t n_max
   if (rc) return rc;
   return apc_segment_plane_nobegin(ctx, xyzi, n_max, n_dev, distance_threshold, ransac_n, num_iterations, probability,
                                    seed, sample_table_dev, out_plane_dev, out_inlier_mask, out_info_dev, nullptr, nullptr,
-                                   4, s, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                   4, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 // Per-hypothesis tallies {inlier count, integer error sum} of the most recent segment_plane call.
