@@ -97,3 +97,174 @@ class SensorSynchronizer:
         for i in ids:
             self.latest[i] = None
         return ids, msgs
+
+
+# ---- the node ------------------------------------------------------------------------------------
+def _quat_to_matrix(t, q) -> np.ndarray:
+    """4x4 float64 from a translation (x, y, z) and a unit quaternion (x, y, z, w)."""
+    x, y, z, w = (float(v) for v in q)
+    T = np.eye(4)
+    T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                 [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                 [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+    T[:3, 3] = [float(v) for v in t]
+    return T
+
+
+def _make_node_class():
+    from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, Duration, ExtrapolationException, Header,
+                              LookupException, Node, PointCloud2, PointField, QoSHistoryPolicy, QoSProfile,
+                              QoSReliabilityPolicy, Time, TransformListener, point_cloud2)
+    from .utils import numpy_struct_to_pointcloud2
+
+    class PointcloudConcatenatorNode(Node):
+        """The node ``pointcloud_concatenator.py:1-5`` describes: n ``PointCloud2`` topics in, one merged
+        cloud out, in ``target_frame`` when one is given (per-sensor TF looked up once and cached, as the
+        preprocessor does for its static transform, ``pp.py:704-732``).
+
+        ``sync_mode='sync'``: with ROS 2 present the sets come from
+        ``message_filters.ApproximateTimeSynchronizer`` (the import the reference already carries,
+        ``pp.py:102``); without it from :class:`SensorSynchronizer` with the same ``slop``.
+        ``sync_mode='robust'``: :class:`SensorSynchronizer` in robust mode - a sensor that has been silent
+        for ``timeout`` seconds no longer holds the output back.
+
+        The merge + per-sensor transform (+ optional voxel grid) is ONE launch chain on the GPU
+        (:func:`concatenate`); the merged records (x, y, z, intensity as float32) are packed on the device
+        and copied to the host once.
+        """
+
+        def __init__(self, node_name='pointcloud_concatenator', **kw):
+            super().__init__(node_name, **kw)
+            self.declare_parameter('input_topics', ['/lidar_front/points', '/lidar_rear/points'])
+            self.declare_parameter('output_topic', '/lidar/points_concatenated')
+            self.declare_parameter('target_frame', '')
+            self.declare_parameter('sync_mode', 'sync')
+            self.declare_parameter('slop', 0.05)
+            self.declare_parameter('timeout', 0.2)
+            self.declare_parameter('queue_size', 10)
+            self.declare_parameter('transform_timeout', 0.1)
+            self.declare_parameter('voxel_size', 0.0)
+            self.declare_parameter('remove_nans', True)
+            self.declare_parameter('qos', 'SENSOR_DATA')
+            gp = lambda n: self.get_parameter(n).value  # noqa: E731
+            self.input_topics = list(gp('input_topics'))
+            if not 1 <= len(self.input_topics) <= _capi.APC_MAX_CLOUDS:
+                raise ValueError(f"input_topics: 1..{_capi.APC_MAX_CLOUDS} sensors")
+            self.target_frame = str(gp('target_frame'))
+            self.sync_mode = str(gp('sync_mode')).lower()
+            self.slop, self.timeout = float(gp('slop')), float(gp('timeout'))
+            self.transform_timeout = float(gp('transform_timeout'))
+            self.voxel_size = float(gp('voxel_size'))
+            self.remove_nans = bool(gp('remove_nans'))
+            qos_name = str(gp('qos')).lower()
+            qos = QoSProfile(reliability=QoSReliabilityPolicy.BEST_EFFORT if qos_name == 'sensor_data'
+                             else QoSReliabilityPolicy.RELIABLE, history=QoSHistoryPolicy.KEEP_LAST, depth=1)
+            self.tf_buffer = Buffer()
+            self.tf_listener = TransformListener(self.tf_buffer, self)
+            self.sensor_tf = [None] * len(self.input_topics)       # cached 4x4 per sensor (static extrinsics)
+            self.frame_count = 0
+            self.pointfields, self.point_step = numpy_struct_to_pointcloud2(
+                ['x', 'y', 'z', 'intensity'], [PointField.FLOAT32] * 4)
+            self._pinned = [None, None]
+            self.pointcloud_pub = self.create_publisher(PointCloud2, str(gp('output_topic')), qos)
+            self.synchronizer = None
+            self.filter_sync = None
+            if self.sync_mode == 'sync' and HAVE_ROS:           # the message_filters seam
+                from message_filters import ApproximateTimeSynchronizer, Subscriber
+                subs = [Subscriber(self, PointCloud2, t, qos_profile=qos) for t in self.input_topics]
+                self.filter_sync = ApproximateTimeSynchronizer(subs, int(gp('queue_size')), self.slop)
+                self.filter_sync.registerCallback(lambda *msgs: self.publish_set(list(range(len(msgs))), list(msgs)))
+                self.subs = subs
+            else:
+                if self.sync_mode not in ('sync', 'robust'):
+                    raise ValueError("sync_mode must be 'sync' or 'robust'")
+                self.synchronizer = SensorSynchronizer(len(self.input_topics), mode=self.sync_mode, slop=self.slop,
+                                                       timeout=self.timeout)
+                self.subs = [self.create_subscription(PointCloud2, t, (lambda m, i=i: self.sensor_callback(i, m)), qos)
+                             for i, t in enumerate(self.input_topics)]
+            self._tf_errors = (LookupException, ConnectivityException, ExtrapolationException)
+            self._Time, self._Duration, self._Header, self._pc2 = Time, Duration, Header, point_cloud2
+
+        # one sensor's message arrived (SensorSynchronizer modes)
+        def sensor_callback(self, sensor: int, msg):
+            ready = self.synchronizer.add(sensor, msg)
+            if ready is not None:
+                self.publish_set(*ready)
+
+        def lookup_sensor_tf(self, sensor: int, frame_id: str, stamp=None):
+            """4x4 sensor frame -> target frame, cached after the first successful lookup."""
+            if not self.target_frame or frame_id == self.target_frame:
+                return None
+            if self.sensor_tf[sensor] is not None:
+                return self.sensor_tf[sensor]
+            tf = self.tf_buffer.lookup_transform(self.target_frame, frame_id, self._Time.from_msg(stamp),
+                                                 self._Duration(seconds=self.transform_timeout))
+            tr, ro = tf.transform.translation, tf.transform.rotation
+            self.sensor_tf[sensor] = _quat_to_matrix((tr.x, tr.y, tr.z), (ro.x, ro.y, ro.z, ro.w))
+            return self.sensor_tf[sensor]
+
+        def publish_set(self, sensor_ids, msgs):
+            """Merge one synchronised set and publish it.  A sensor whose transform cannot be resolved
+            is left out of this set (robust behaviour) rather than published in the wrong frame."""
+            if self.pointcloud_pub.get_subscription_count() == 0:
+                return None
+            clouds, transforms = [], []
+            for i, m in zip(sensor_ids, msgs):
+                if m.width * m.height == 0:
+                    continue
+                try:
+                    T = self.lookup_sensor_tf(i, m.header.frame_id, m.header.stamp)
+                except self._tf_errors as e:
+                    self.get_logger().warn(f"no transform {m.header.frame_id} -> {self.target_frame}: {e}; sensor {i} skipped",
+                                           throttle_duration_sec=2.0)
+                    continue
+                clouds.append(m)
+                transforms.append(T)
+            if not clouds:
+                return None
+            stages = dict(voxel_size=self.voxel_size) if self.voxel_size > 0.0 else None
+            filter_kw = dict(skip_nans=self.remove_nans, remove_nan=self.remove_nans, remove_inf=self.remove_nans)
+            xyzi, n, _ = concatenate(clouds, transforms, filter_kw=filter_kw, stages=stages)
+            ctx = geometry.get_context(max(n, 1))
+            fields = [(f.offset, f.datatype, src, None) for f, src in zip(self.pointfields, (1, 2, 3, 4))]
+            raw = ctx.repack(xyzi.contiguous(), fields, self.point_step) if n else torch.zeros(0, dtype=torch.uint8)
+            nbytes = n * self.point_step
+            slot = self.frame_count & 1
+            if self._pinned[slot] is None or self._pinned[slot].numel() < nbytes:
+                self._pinned[slot] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+            if n:
+                self._pinned[slot][:nbytes].copy_(raw[:nbytes], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            dt = np.dtype({'names': ['x', 'y', 'z', 'intensity'], 'formats': ['<f4'] * 4, 'offsets': [0, 4, 8, 12],
+                           'itemsize': self.point_step})
+            records = np.frombuffer(self._pinned[slot].numpy(), dtype=dt, count=n)
+            newest = max(msgs, key=SensorSynchronizer._stamp)
+            header = self._Header()
+            header.stamp = newest.header.stamp
+            header.frame_id = self.target_frame or clouds[0].header.frame_id
+            out = self._pc2.create_cloud(header, self.pointfields, records)
+            out.is_dense = bool(self.remove_nans)
+            self.pointcloud_pub.publish(out)
+            self.frame_count += 1
+            return out
+
+    return PointcloudConcatenatorNode
+
+
+def __getattr__(name):                      # the node class needs the ROS seam: built on first use
+    if name == "PointcloudConcatenatorNode":
+        cls = _make_node_class()
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)
+
+
+def main(args=None):                        # pragma: no cover - needs a ROS 2 installation
+    from ._ros_compat import rclpy
+    rclpy.init(args=args)
+    node = __getattr__("PointcloudConcatenatorNode")()
+    try:
+        rclpy.spin(node)
+    finally:
+        node.destroy_node()
+        rclpy.shutdown()

@@ -111,7 +111,32 @@ def full_capture():
     return traffic
 
 
+def steady_capture():
+    """gpurun_out/steady_kernels_TAG.csv (profiles/steady_traffic.sh: the 8-lane bench under ncu kernel replay,
+    --cache-control none, two DRAM counters = one pass per kernel) -> profiles/TAG_steady_traffic.json"""
+    import collections
+    path = os.path.join(GP, f"steady_kernels_{tag}.csv")
+    rows = [l for l in open(path) if l.startswith('"')]
+    agg = collections.defaultdict(lambda: collections.defaultdict(list))
+    for r in csv.DictReader(io.StringIO("".join(rows))):
+        v = float(r["Metric Value"].replace(",", "") or 0) * UNIT_BYTES.get(r["Metric Unit"], 1.0)
+        agg[short(r["Kernel Name"])][r["Metric Name"]].append(v)
+    mean = lambda xs: sum(xs) / max(len(xs), 1)
+    per = {k: {"launches": len(d["dram__bytes_read.sum"]), "dram_read": round(mean(d["dram__bytes_read.sum"])),
+               "dram_write": round(mean(d["dram__bytes_write.sum"])),
+               "l2_hit_pct": round(mean(d["lts__t_sector_hit_rate.pct"]), 1)} for k, d in agg.items() if k.startswith("k_")}
+    json.dump({"source": f"ncu kernel replay of the 8-lane bench (64 resident frames), --cache-control none --clock-control none, {tag}: "
+                         "launches serialised, L2 left as the other lanes' kernels left it (steady state); write-backs are "
+                         "charged to the kernel that evicts them",
+               "dram_bytes_per_launch": {k: v["dram_read"] + v["dram_write"] for k, v in per.items()},
+               "per_kernel": per,
+               "MB_per_scan": round(sum(v["dram_read"] + v["dram_write"] for v in per.values()) / 1e6, 2)},
+              open(os.path.join(OUT, f"{tag}_steady_traffic.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if os.path.exists(os.path.join(GP, f"steady_kernels_{tag}.csv")):
+        steady_capture()
     if os.path.exists(os.path.join(GP, f"launches_{tag}.csv")):
         launch_shares()
     if os.path.exists(os.path.join(GP, f"prof_{tag}.ncu-rep")):

@@ -199,6 +199,48 @@ def test_concatenate_then_voxel():
     assert np.array_equal(xyzi.cpu().numpy()[:, :3].view(np.uint32), ref["positions"].view(np.uint32))
 
 
+def test_concatenator_node_publishes_the_merged_cloud():
+    """Three sensors with different layouts and extrinsics through PointcloudConcatenatorNode: the
+    published PointCloud2 (x, y, z, intensity, frame = target_frame, stamp = newest of the set) holds
+    the oracle's concatenation bit for bit; a sensor without a transform is left out, not misplaced."""
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_concatenator as pcn
+    from autodriver_pointcloud_preprocessor_b200 import synth
+    from autodriver_pointcloud_preprocessor_b200.msgs import Time
+    from oracle import pc2
+    from oracle import pipeline as opipe
+    layouts = ["xyzi16", "xyzirt22", "ouster48"]
+    scans = [synth.lidar_scan(seed=70 + s, n_beams=16, n_az=256, nan_frac=0.0) for s in range(3)]
+    msgs = [synth.pack_cloud(sc, lay, frame_id=f"lidar{s}") for s, (sc, lay) in enumerate(zip(scans, layouts))]
+    for s, m in enumerate(msgs):
+        m.header.stamp = Time(100, 10_000_000 * s)
+    node = pcn.PointcloudConcatenatorNode(parameter_overrides={
+        "input_topics": ["/l0/points", "/l1/points", "/l2/points"], "target_frame": "base_link", "sync_mode": "sync"})
+    quats = [(0.0, 0.0, np.sin(a / 2), np.cos(a / 2)) for a in (0.3, -1.2, 2.0)]
+    trans = [(1.5, 0.0, 1.8), (-1.0, 0.5, 1.7), (0.0, -0.8, 2.0)]
+    for s in range(3):
+        node.tf_buffer.set_transform("base_link", f"lidar{s}", trans[s], quats[s])
+    for s in range(3):
+        node.subs[s][1](msgs[s])
+    assert len(node.pointcloud_pub.messages) == 1
+    out = node.pointcloud_pub.messages[0]
+    assert out.header.frame_id == "base_link" and (out.header.stamp.sec, out.header.stamp.nanosec) == (100, 20_000_000)
+    assert [(f.name, f.offset, f.datatype) for f in out.fields] == [("x", 0, 7), ("y", 4, 7), ("z", 8, 7), ("intensity", 12, 7)]
+    Ts = [pcn._quat_to_matrix(trans[s], quats[s]).astype(np.float32) for s in range(3)]
+    ref = opipe.concat(scans, Ts)
+    arr = np.frombuffer(out.data, dtype=pc2.dtype_from_fields(out.fields, out.point_step))
+    assert out.width == ref["positions"].shape[0]
+    got = np.stack([arr["x"], arr["y"], arr["z"]], 1)
+    assert np.array_equal(got.view(np.uint32), ref["positions"].view(np.uint32))
+    assert np.array_equal(arr["intensity"].view(np.uint32), ref["intensity"].view(np.uint32))
+    # a sensor whose frame is unknown to TF is skipped (robust), the others still go out
+    msgs[1].header.frame_id = "unknown"
+    node.sensor_tf[1] = None
+    for s in range(3):
+        node.subs[s][1](msgs[s])
+    out2 = node.pointcloud_pub.messages[-1]
+    assert out2.width == scans[0]["positions"].shape[0] + scans[2]["positions"].shape[0]
+
+
 @pytest.mark.parametrize("layout,fused,backend", [("xyzi16", "auto", "open3d"), ("xyzirt22", "auto", "numpy"),
                                                   ("xyzirt22", "true", "torch")])
 def test_node_callback_with_normals_and_reference_backends(layout, fused, backend):

@@ -123,6 +123,49 @@ def test_sensor_synchronizer():
     assert out is not None and out[0] == [0, 1]
 
 
+def test_concatenator_node_policies():
+    """PointcloudConcatenatorNode (pointcloud_concatenator.py:1-5): parameters, one subscription per
+    sensor, sets handed to publish_set by the two policies, per-sensor TF looked up with Duration / Time
+    and cached.  No GPU: the merge itself is stubbed out here (tests/test_gpu_dropin.py runs it)."""
+    from autodriver_pointcloud_preprocessor_b200 import pointcloud_concatenator as pcn
+    from autodriver_pointcloud_preprocessor_b200.msgs import Header, PointCloud2, Time
+
+    def msg(t, frame):
+        return PointCloud2(header=Header(stamp=Time(int(t), int((t % 1) * 1e9)), frame_id=frame), width=1, height=1)
+
+    sets = []
+    Node = pcn.PointcloudConcatenatorNode
+    node = Node(parameter_overrides={"input_topics": ["/a/points", "/b/points", "/c/points"], "target_frame": "base_link",
+                                     "sync_mode": "sync", "slop": 0.05})
+    node.publish_set = lambda ids, msgs: sets.append((ids, [m.header.frame_id for m in msgs]))
+    assert [s[0] for s in node.subs] == ["/a/points", "/b/points", "/c/points"]
+    assert node.pointcloud_pub.topic == "/lidar/points_concatenated"
+    for i, fr in enumerate("abc"):
+        node.subs[i][1](msg(5.0 + 0.01 * i, fr))               # the subscription callbacks
+    assert sets == [([0, 1, 2], ["a", "b", "c"])]
+    node.subs[0][1](msg(6.0, "a"))
+    node.subs[1][1](msg(6.2, "b"))
+    node.subs[2][1](msg(6.21, "c"))                             # a's message is outside the slop: no set
+    assert len(sets) == 1
+    robust = Node(parameter_overrides={"input_topics": ["/a/points", "/b/points"], "sync_mode": "robust", "timeout": 0.2})
+    robust.publish_set = lambda ids, msgs: sets.append((ids, None))
+    robust.subs[0][1](msg(1.0, "a"))
+    robust.subs[0][1](msg(1.1, "a"))                            # sensor b is dead: a alone is published
+    assert [s[0] for s in sets[1:]] == [[0], [0]]
+    # TF: target == sensor frame needs none; otherwise one lookup, cached
+    assert node.lookup_sensor_tf(0, "base_link") is None
+    node.tf_buffer.set_transform("base_link", "a", (1.0, 2.0, 3.0), (0.0, 0.0, 0.0, 1.0))
+    T = node.lookup_sensor_tf(0, "a", Time(1, 0))
+    assert T.shape == (4, 4) and T[:3, 3].tolist() == [1.0, 2.0, 3.0] and node.lookup_sensor_tf(0, "a") is T
+    with pytest.raises(Exception):
+        node.lookup_sensor_tf(1, "b")                           # unknown frame: tf2 LookupException
+    with pytest.raises(ValueError):
+        Node(parameter_overrides={"input_topics": [f"/s{i}" for i in range(9)]})
+    # quaternion -> matrix: 90 degrees about z
+    R = pcn._quat_to_matrix((0, 0, 0), (0.0, 0.0, np.sin(np.pi / 4), np.cos(np.pi / 4)))
+    assert np.allclose(R[:3, :3] @ [1.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+
+
 def test_shard_frames_covers_everything():
     from autodriver_pointcloud_preprocessor_b200.replay import shard_frames
     for n, w in ((1024, 8), (1024, 3), (5, 8), (0, 2)):
