@@ -492,7 +492,7 @@ struct TopK {
 #define KNN_WARPS 4
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float* __restrict__ avg,
-            uint32_t* __restrict__ stragglers, ApcCtrl* ctrl) {
+            uint32_t* __restrict__ stragglers, ApcCtrl* ctrl, uint32_t start_fill, int exact_margin, uint32_t merge_min) {
   __shared__ uint32_t s_buf[KNN_WARPS][KNN_CAP];
   const uint32_t n = apc_count(n_dev, n_max);
   const uint32_t n_sorted = grid_sorted_count(g, ctrl, n);
@@ -505,7 +505,20 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
     const float4 q = g.sorted[j];
     const uint32_t orig = __float_as_uint(q.w);
     bool done = false;
-    for (uint32_t level = 0; level < g.levels && !done; ++level) {
+    // Optional starting level (start_fill > 0, an A/B knob that lost): the finest level whose OWN cell already
+    // holds start_fill points (lane l reads the population of the query's cell at level l through the slot
+    // recorded at insert time: two dependent loads for all levels at once).
+    uint32_t level0 = 0;
+    if (start_fill) {
+      uint32_t fill = 0;
+      if (lane < g.levels) {
+        const uint32_t sl = g.slot[(size_t)lane * n_max + orig];
+        if (sl != GRID_NOSLOT) fill = g.slots[sl].fill;
+      }
+      const uint32_t okm = __ballot_sync(0xffffffffu, fill >= start_fill);
+      level0 = okm ? (uint32_t)__ffs(okm) - 1u : g.levels - 1u;
+    }
+    for (uint32_t level = level0; level < g.levels && !done; ++level) {
       const float c = g.cell[level];
       int32_t ix, iy, iz;
       if (!grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz)) continue;
@@ -526,7 +539,16 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
       const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
       if (total < k_eff) continue;
       const float4* sp = g.sorted + (size_t)level * n_max;
-      const float safe = __fmul_rn(c, 0.999f);   // every point closer than ~c lies inside the block
+      // every point closer than `safe` lies inside the 27-cell block: the cell edge plus (exact_margin) the
+      // query's distance to the nearest face of its own cell, less 0.1 % for the rounding of the cell index
+      float safe = c;
+      if (exact_margin) {
+        const float mx = fminf(__fsub_rn(q.x, __fmul_rn((float)ix, c)), __fsub_rn(__fmul_rn((float)(ix + 1), c), q.x));
+        const float my = fminf(__fsub_rn(q.y, __fmul_rn((float)iy, c)), __fsub_rn(__fmul_rn((float)(iy + 1), c), q.y));
+        const float mz = fminf(__fsub_rn(q.z, __fmul_rn((float)iz, c)), __fsub_rn(__fmul_rn((float)(iz + 1), c), q.z));
+        safe = __fadd_rn(c, fmaxf(0.0f, fminf(mx, fminf(my, mz))));
+      }
+      safe = __fmul_rn(safe, 0.999f);
       if (k_eff <= 32u) {
         // 2'. k <= 32 (the reference's default is 20): the k best live in REGISTERS, lane i holding the
         // i-th smallest distance so far.  A batch of 32 candidates is screened with one ballot against
@@ -551,6 +573,32 @@ k_knn_query(uint32_t n_max, const uint32_t* n_dev, GridDev g, uint32_t k, float*
             d2 = d2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
           }
           uint32_t cand = __ballot_sync(0xffffffffu, d2 < kth);
+          if ((uint32_t)__popc(cand) > merge_min) {
+            // many of the batch beat the current k-th value (always the first batch of a pass, often the second):
+            // sort the batch across the lanes (bitonic network, 15 shuffle stages) and merge it with the sorted
+            // `val` - reversed batch, element-wise minimum = the 32 smallest of the union as a bitonic sequence,
+            // 5 more stages put them in order.  ~100 instructions whatever the number of newcomers, against ~14
+            // per one-by-one insertion below (the first batch alone used to cost 450).
+            float w = d2;
+#pragma unroll
+            for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+              for (uint32_t jj = kk >> 1; jj > 0; jj >>= 1) {
+                const float o = __shfl_xor_sync(0xffffffffu, w, jj);
+                const bool take_min = ((lane & kk) == 0) == ((lane & jj) == 0);
+                w = take_min ? fminf(w, o) : fmaxf(w, o);
+              }
+            }
+            float mrg = fminf(val, __shfl_sync(0xffffffffu, w, 31u - lane));
+#pragma unroll
+            for (uint32_t jj = 16; jj > 0; jj >>= 1) {
+              const float o = __shfl_xor_sync(0xffffffffu, mrg, jj);
+              mrg = (lane & jj) == 0 ? fminf(mrg, o) : fmaxf(mrg, o);
+            }
+            val = mrg;
+            kth = __shfl_sync(0xffffffffu, val, k_eff - 1u);
+            cand = 0;
+          }
           while (cand) {
             const uint32_t b = __ffs(cand) - 1u;
             cand &= cand - 1u;
@@ -1055,7 +1103,17 @@ int apc_statistical_nobegin(apc_ctx* ctx, const float* xyzi, uint32_t n_max, con
   const uint32_t bq = min(apc_div_up(n_max, KNN_WARPS), (uint32_t)APC_SM_COUNT * 16);   // one warp per query, grid-stride
   {
     APC_PROF(ctx, "k_knn_query", s);
-    k_knn_query<<<bq, KNN_WARPS * 32, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl);
+    // APC_KNN_START_FILL: own-cell population that selects the starting level (default 0 = always level 0: skipping
+    // fine levels by this estimate examines more candidates than the failed passes cost - 2.49 / 2.94 / 3.34 ms
+    // against 1.86 ms for a population of 5 / 10 / 16 on the C4 scan);
+    // APC_KNN_MARGIN=0: guaranteed radius = the cell edge only (profiles/r2x_knn_ab.json)
+    static const int fill_env = []() { const char* e = getenv("APC_KNN_START_FILL"); return e ? atoi(e) : -1; }();
+    static const int margin_env = []() { const char* e = getenv("APC_KNN_MARGIN"); return e ? atoi(e) : 1; }();
+    const uint32_t start_fill = fill_env > 0 ? (uint32_t)fill_env : 0u;
+    // newcomers in a batch of 32 above which the batch is sorted and merged instead of inserted one by one
+    static const uint32_t merge_min = []() { const char* e = getenv("APC_KNN_MERGE_MIN"); return e ? (uint32_t)atoi(e) : 6u; }();
+    k_knn_query<<<bq, KNN_WARPS * 32, 0, s>>>(n_max, n_dev, g.d, (uint32_t)nb_neighbors, avg, sc->stragglers, ctx->ctrl,
+                                              start_fill, margin_env, merge_min);
   }
   {
     APC_PROF(ctx, "k_knn_stragglers", s);

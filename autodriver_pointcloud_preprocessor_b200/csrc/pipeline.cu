@@ -146,7 +146,8 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
     // level-0 cell such that the k nearest of a point on a voxelised surface (one point per
     // voxel_size^2: r_k = voxel_size * sqrt(k / pi)) usually lie inside the first 27-cell block; the
     // result does not depend on it (the query climbs levels until the k-th distance is covered)
-    const float hint = has_vox ? cfg->voxel_size * fmaxf(2.0f, 1.3f * sqrtf((float)cfg->stat_nb_neighbors / 3.14159265f)) : 0.0f;
+    static const float hint_scale = []() { const char* e = getenv("APC_KNN_HINT"); return e ? (float)atof(e) : 1.25f; }();   // A/B knob (profiles/r2x_knn_ab.json)
+    const float hint = has_vox ? hint_scale * cfg->voxel_size * fmaxf(2.0f, 1.3f * sqrtf((float)cfg->stat_nb_neighbors / 3.14159265f)) : 0.0f;
     rc = apc_statistical_nobegin(ctx, cur, n_total, dc + cur_cnt, cfg->stat_nb_neighbors, cfg->stat_std_ratio, hint,
                                  ctx->mask_a, nullptr, nullptr, s);
     if (rc) return rc;
