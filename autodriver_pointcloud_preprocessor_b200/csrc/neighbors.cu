@@ -1388,14 +1388,46 @@ k_normals_cov(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r2, uint32
       }
       const uint32_t rs = __shfl_sync(0xffffffffu, cs, run), rp = __shfl_sync(0xffffffffu, ps, run);
       const uint32_t pos = rs + (flat - rp);
+      // key = (d2 bits : 32 | original index : 26 | tag : 6), ordered by (d2, index) like the oracle; the tag (the
+      // lane that holds the entry's sorted position) only rides along through the sorting network below
       unsigned long long key = ~0ull;
       if (ci < total) {
         const float4 p = g.sorted[pos];
         const float d2 = d2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
-        if (d2 <= r2) key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+        if (d2 <= r2) key = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)__float_as_uint(p.w) << 6) | lane;
       }
       in_radius += __popc(__ballot_sync(0xffffffffu, key != ~0ull));
       uint32_t cand = __ballot_sync(0xffffffffu, key < kth);
+      if ((uint32_t)__popc(cand) > 6u) {
+        // many newcomers (dense clouds: the reference's default 0.01 m voxels leave 10 - 30 points within 0.1 m):
+        // sort the batch across the lanes (bitonic network on the 64-bit keys) and merge it with the sorted `kv`,
+        // ~160 instructions whatever their number against ~25 per one-by-one insertion - 55 % of this kernel's
+        // instructions were that insertion loop (profiles/r2y_normals_ab.json).  Same order, same bits.
+        unsigned long long w = key;
+#pragma unroll
+        for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+          for (uint32_t jj = kk >> 1; jj > 0; jj >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, w, jj);
+            const bool take_min = ((lane & kk) == 0) == ((lane & jj) == 0);
+            w = (take_min == (o < w)) ? o : w;
+          }
+        }
+        const unsigned long long old = (kv & ~63ull) | (32u + lane);       // entries of kv: tag = 32 + their lane
+        const unsigned long long wr = __shfl_sync(0xffffffffu, w, 31u - lane);
+        unsigned long long mrg = wr < old ? wr : old;
+#pragma unroll
+        for (uint32_t jj = 16; jj > 0; jj >>= 1) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, mrg, jj);
+          mrg = (((lane & jj) == 0) == (o < mrg)) ? o : mrg;
+        }
+        const uint32_t tag = (uint32_t)mrg & 63u;
+        const uint32_t from_new = __shfl_sync(0xffffffffu, pos, tag & 31u), from_old = __shfl_sync(0xffffffffu, pv, tag & 31u);
+        pv = tag < 32u ? from_new : from_old;
+        kv = mrg;
+        kth = __shfl_sync(0xffffffffu, kv, max_nn - 1u);
+        cand = 0;
+      }
       while (cand) {
         const uint32_t b = __ffs(cand) - 1u;
         cand &= cand - 1u;
