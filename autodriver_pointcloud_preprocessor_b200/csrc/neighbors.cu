@@ -16,6 +16,7 @@
 // are (fewer than k points in range of the coarsest level) fall to an exact brute-force
 // kernel.  The table is cleaned by the points that own rank 0 of their cell, not by memset.
 #include <cstdlib>
+#include <cstring>
 #include "apc_scan.cuh"
 #include "apc_grid.cuh"
 APC_TRACE_EXPORT(neighbors)
@@ -367,6 +368,151 @@ k_radius_query_oct(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r, fl
   APC_STAMP(0, 1);
 }
 
+// Decision-only variant (keep iff >= nb_points within r) - an A/B knob that lost, see radius_decide.  The per-thread walk above
+// costs what its SLOWEST lane costs: two thirds of its warp instructions were the own-cell loop running on for
+// the one or two lanes of a warp that do not find nb_points near themselves (profiles/r2v_ncu_full.csv,
+// hot_lines).  Here every lane scans outwards for at most `own_rounds` rounds (8 records); the lanes still
+// short of nb_points are then served by the WHOLE WARP, one after the other: the rest of the lane's own cell
+// 32 records at a time (ballot + popc), then lanes 1..7 resolve the <= 7 box-pruned neighbour cells in one
+// round trip and the warp walks their runs as one flat list.  A warp with more than `coop_max` such lanes
+// (a sparse region: everybody is short) lets them walk alone as before - there the per-thread walk keeps all
+// lanes busy.  Counts may overshoot nb_points (whole batches are counted); the decision is the same.
+__global__ void __launch_bounds__(128)
+k_radius_decide_oct(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r, float r2, uint32_t nb_points,
+                    uint8_t* __restrict__ mask, const ApcCtrl* __restrict__ ctrl, uint32_t own_rounds, uint32_t coop_max) {
+  pdl_enter();
+  const uint32_t n = grid_sorted_count(g, ctrl, apc_count(n_dev, n_max));
+  const float c = grid_cell_size(g, 0);
+  const uint32_t lane = lane_id();
+  const float reach = r * 1.00001f, reach2 = __fmul_rn(reach, reach);
+  APC_STAMP(0, 0);
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t j = base + threadIdx.x;
+    const bool live = j < n;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t ix = 0, iy = 0, iz = 0;
+    uint32_t cnt = 0, b = 0, e = 0, up = 0, down = 0;
+    bool pending = false;
+    if (live) {
+      q = g.sorted[j];
+      grid_coord_g(g, c, q.x, q.y, q.z, ix, iy, iz);  // succeeded at insert time
+      uint32_t f;
+      if (grid_lookup(g, grid_key(0, ix, iy, iz), b, f) && j >= b && j < b + f) {
+        e = b + f;
+        cnt = 1u;                                   // q itself
+        up = j + 1;
+        down = j;
+        for (uint32_t round = 0; round < own_rounds && cnt < nb_points && (up < e || down > b); ++round) {
+          float4 p[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            ok[u] = up + u < e;
+            p[u] = g.sorted[ok[u] ? up + u : j];
+            ok[2 + u] = down >= b + 1 + u;
+            p[2 + u] = g.sorted[ok[2 + u] ? down - 1 - u : j];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cnt += (ok[u] && d2_f32(q.x, q.y, q.z, p[u].x, p[u].y, p[u].z) <= r2) ? 1u : 0u;
+          up = min(up + 2, e);
+          down = down >= b + 2 ? down - 2 : b;
+        }
+        pending = cnt < nb_points;
+      } else {
+        cnt = radius_count_oct(g, c, q, j, r, r2, nb_points, 0);   // (a record outside its own cell's run: not reachable)
+      }
+    }
+    uint32_t bal = __ballot_sync(0xffffffffu, pending);
+    if (bal && (uint32_t)__popc(bal) <= coop_max) {
+      while (bal) {
+        const uint32_t L = __ffs(bal) - 1u;
+        bal &= bal - 1u;
+        const float qx = __shfl_sync(0xffffffffu, q.x, L), qy = __shfl_sync(0xffffffffu, q.y, L), qz = __shfl_sync(0xffffffffu, q.z, L);
+        uint32_t cL = __shfl_sync(0xffffffffu, cnt, L);
+        const uint32_t bL = __shfl_sync(0xffffffffu, b, L), eL = __shfl_sync(0xffffffffu, e, L);
+        const uint32_t upL = __shfl_sync(0xffffffffu, up, L), downL = __shfl_sync(0xffffffffu, down, L);
+        const int32_t ixL = __shfl_sync(0xffffffffu, ix, L), iyL = __shfl_sync(0xffffffffu, iy, L), izL = __shfl_sync(0xffffffffu, iz, L);
+        // 1. what is left of the own cell: [bL, downL) and [upL, eL)
+        const uint32_t lo_n = downL - bL, tot = lo_n + (eL - upL);
+        for (uint32_t t0 = 0; t0 < tot && cL < nb_points; t0 += 32) {
+          const uint32_t t = t0 + lane;
+          bool hit = false;
+          if (t < tot) {
+            const float4 p = g.sorted[t < lo_n ? bL + t : upL + (t - lo_n)];
+            hit = d2_f32(qx, qy, qz, p.x, p.y, p.z) <= r2;
+          }
+          cL += __popc(__ballot_sync(0xffffffffu, hit));
+        }
+        if (cL < nb_points) {
+          // 2. the neighbour cells the ball reaches (same pruning as radius_count_oct)
+          const float qa[3] = {qx, qy, qz};
+          const int32_t ia[3] = {ixL, iyL, izL};
+          int32_t dir[3];
+          float gap2[3];
+          bool both = false;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float lo = __fmul_rn((float)ia[a], c), hi = __fmul_rn((float)(ia[a] + 1), c);
+            const float slack = 1e-6f * (fabsf(qa[a]) + c) + 1e-5f * r;
+            const float gl = fmaxf(0.0f, __fsub_rn(__fsub_rn(qa[a], lo), slack)), gh = fmaxf(0.0f, __fsub_rn(__fsub_rn(hi, qa[a]), slack));
+            dir[a] = gl <= gh ? -1 : 1;
+            const float gmin = fminf(gl, gh);
+            gap2[a] = __fmul_rn(gmin, gmin);
+            both |= fmaxf(gl, gh) <= reach;
+          }
+          if (both) {                                 // slack not small against r: the lane walks all 27 cells itself
+            uint32_t full = 0;
+            if (lane == L) full = radius_count(g, c, q, r2, nb_points, 0, 27);
+            cL = __shfl_sync(0xffffffffu, full, L);
+          } else {
+            uint32_t ns = 0, nf = 0;
+            if (lane >= 1u && lane < 8u) {
+              const float s2 = ((lane & 1u) ? gap2[0] : 0.0f) + ((lane & 2u) ? gap2[1] : 0.0f) + ((lane & 4u) ? gap2[2] : 0.0f);
+              if (s2 <= reach2) {
+                const uint64_t key = grid_key(0, ixL + ((lane & 1u) ? dir[0] : 0), iyL + ((lane & 2u) ? dir[1] : 0),
+                                              izL + ((lane & 4u) ? dir[2] : 0));
+                uint32_t bb, ff;
+                if (grid_lookup(g, key, bb, ff)) { ns = bb; nf = ff; }
+              }
+            }
+            uint32_t incl = nf;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= (uint32_t)o) incl += v;
+            }
+            const uint32_t ps = incl - nf;                       // first flat index of lane's run
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
+            for (uint32_t t0 = 0; t0 < total && cL < nb_points; t0 += 32) {
+              const uint32_t t = t0 + lane;
+              const uint32_t flat = min(t, total - 1u);
+              uint32_t run = 0;                                  // largest m in 1..7 with ps[m] <= flat
+#pragma unroll
+              for (int step = 4; step > 0; step >>= 1) {
+                const uint32_t mid = run + step;
+                const uint32_t v = __shfl_sync(0xffffffffu, ps, mid & 31u);
+                if (mid < 8u && v <= flat) run = mid;
+              }
+              const uint32_t rs = __shfl_sync(0xffffffffu, ns, run), rp = __shfl_sync(0xffffffffu, ps, run);
+              bool hit = false;
+              if (t < total) {
+                const float4 p = g.sorted[rs + (flat - rp)];
+                hit = d2_f32(qx, qy, qz, p.x, p.y, p.z) <= r2;
+              }
+              cL += __popc(__ballot_sync(0xffffffffu, hit));
+            }
+          }
+        }
+        if (lane == L) cnt = cL;
+      }
+    } else if (pending) {
+      cnt = radius_count_oct(g, c, q, j, r, r2, nb_points, 0);
+    }
+    if (live) mask[__float_as_uint(q.w)] = cnt >= nb_points ? 1 : 0;
+  }
+  APC_STAMP(0, 1);
+}
+
 // Cell edge of the radius grid in units of r (+ 2^-10 slack so that d2 <= r2 never reaches past the
 // neighbouring cell): >= 2 = the pruned 8-cell walk above (default 2), 1 = the 27-cell walk (APC_RADIUS_CELL).
 static float radius_cell_mult() {
@@ -431,8 +577,20 @@ static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const u
   static const bool split = []() { const char* e = getenv("APC_RADIUS_SPLIT"); return e && atoi(e) != 0; }();
   const uint32_t bq = min(apc_div_up(n_max, 128), (uint32_t)APC_SM_COUNT * 16);
   if (radius_cell_mult() >= 2.0f) {
+    // APC_RADIUS_COOP = "own_rounds,coop_max": warp-cooperative service of the lanes left short (k_radius_decide_oct).
+    // Default coop_max = 0 = the per-thread walk k_radius_query_oct: the cooperative variant LOST the A/B (24.3 vs
+    // 21.9 us alone, 67.7 vs 64.8 us/scan with all lanes busy at 2,8; 33.4 us at 2,32; profiles/r2p_radius_ab.json)
+    static const uint32_t own_rounds = []() { const char* e = getenv("APC_RADIUS_COOP"); return e ? (uint32_t)atoi(e) : 2u; }();
+    static const uint32_t coop_max = []() {
+      const char* e = getenv("APC_RADIUS_COOP");
+      const char* comma = e ? strchr(e, ',') : nullptr;
+      return comma ? (uint32_t)atoi(comma + 1) : 0u;
+    }();
     APC_PROF(ctx, "k_radius_query", s);
-    apc_klaunch(ctx, k_radius_query_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    if (coop_max)
+      apc_klaunch(ctx, k_radius_decide_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, mask, ctx->ctrl, own_rounds, coop_max);
+    else
+      apc_klaunch(ctx, k_radius_query_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
     APC_LAUNCH_CHECK(ctx, "k_radius_query_oct");
     return APC_OK;
   }
