@@ -181,7 +181,11 @@ class ScanPipeline:
     def process_host(self, frames, keep_outputs: bool = True):
         """``frames``: pinned uint8 host tensors (one PointCloud2 ``data`` buffer each).
         Returns ``(outputs, counts, d2h_bytes)``: per frame a float32 [n_out, 4] numpy array
-        (x, y, z, intensity) and the 8 pipeline counters.
+        (x, y, z, intensity) and the 8 pipeline counters.  ``keep_outputs``: ``True`` = every output is an
+        owned copy; ``"view"`` = a view of the lane's pinned output buffer, valid until that lane's next
+        frame (at most ``lanes`` frames per call: what a node publishing one scan at a time needs - the
+        message constructor copies the records anyway, pp.py:769); ``False`` = outputs stay in the
+        pinned buffers and ``None`` is returned for them.
 
         Software-pipelined per lane so that the host thread never waits for a copy it has just
         issued: visiting a lane (1) harvests the payload copy issued two visits ago, (2) reads the
@@ -189,6 +193,8 @@ class ScanPipeline:
         finish) and issues the device->host copy of exactly the surviving rows, (3) issues the
         next frame's upload + graph + counters read-back.  H2D, kernels and D2H of different
         frames overlap across lanes."""
+        if keep_outputs == "view" and len(frames) > len(self.lanes):
+            raise ValueError("keep_outputs='view': at most one frame per lane per call")
         results = [None] * len(frames)
         counts = np.zeros((len(frames), 8), dtype=np.int32)
         self._d2h_bytes = 0
@@ -232,7 +238,9 @@ class ScanPipeline:
             return
         f, n = ln.pending[1]
         ln.copy_event.synchronize()
-        if keep_outputs:
+        if keep_outputs == "view":
+            results[f] = ln.h_out[:n].numpy()
+        elif keep_outputs:
             results[f] = ln.h_out[:n].numpy().copy()
         ln.pending[1] = None
 

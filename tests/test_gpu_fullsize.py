@@ -134,6 +134,12 @@ def test_c5_batched_replay_matches_single_shot(big):
             assert counts[f, capi.CNT_STATUS] == 0
             assert np.array_equal(outs[f].view(np.uint32), want[f].view(np.uint32)), (rep, f)
         assert d2h == sum(w.shape[0] * 16 + 32 for w in want)
+    # views of the lanes' pinned output buffers: one frame per lane per call
+    outs, _, _ = pipe.process_host(h_frames[:3], keep_outputs="view")
+    for f in range(3):
+        assert not outs[f].flags.owndata and np.array_equal(outs[f].view(np.uint32), want[f].view(np.uint32)), f
+    with pytest.raises(ValueError):
+        pipe.process_host(h_frames, keep_outputs="view")
     pool = torch.stack([h.cuda() for h in h_frames])
     arena = torch.zeros((len(msgs), bench.N_POINTS, 4), device="cuda")
     carena = torch.zeros((len(msgs), 8), dtype=torch.int32, device="cuda")
