@@ -301,6 +301,26 @@ class PointcloudPreprocessorNode(Node):
         return not (self.estimate_normals and self.estimate_normals_max_neighbors > 64)
 
     # ------------------------------------------------------------------------------------------------
+    def _upload_message(self, ros_cloud):
+        """The message's records as one device uint8 buffer.  Tightly packed rows (the usual case) go
+        bytes -> a pinned staging buffer kept across frames (one host memcpy) -> one asynchronous copy
+        into a device buffer kept across frames; the reference's path through a pageable tensor costs a
+        second host copy and a staged transfer (0.50 -> see profiles/node_times.py).  Padded rows
+        (row_step > width * point_step) are compacted first, like read_points."""
+        n_bytes = ros_cloud.width * ros_cloud.height * ros_cloud.point_step
+        tight = int(getattr(ros_cloud, 'row_step', 0) or 0) in (0, ros_cloud.width * ros_cloud.point_step)
+        if n_bytes == 0 or not tight or len(ros_cloud.data) < n_bytes:
+            return packed_message_bytes(ros_cloud).cuda()
+        stage = getattr(self, '_pinned_in', None)
+        if stage is None or stage.numel() < n_bytes:
+            cap = max(n_bytes + n_bytes // 4, 1 << 20)
+            stage = self._pinned_in = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self._dev_in = torch.empty(cap, dtype=torch.uint8, device='cuda')
+        stage.numpy()[:n_bytes] = np.frombuffer(ros_cloud.data, dtype=np.uint8, count=n_bytes)
+        dev = self._dev_in[:n_bytes]
+        dev.copy_(stage[:n_bytes], non_blocking=True)
+        return dev
+
     def extract_pointcloud(self, ros_cloud):
         """pp.py:394-445: message -> device-resident carrier.  Returns None on every path, like
         the reference."""
@@ -311,7 +331,7 @@ class PointcloudPreprocessorNode(Node):
             self._fused_xyzi = None
             n = ros_cloud.width * ros_cloud.height
             # one upload of the message bytes per scan; both paths read this device buffer
-            self._raw_dev = packed_message_bytes(ros_cloud).cuda()      # row padding (row_step) removed on the way up
+            self._raw_dev = self._upload_message(ros_cloud)
             names = tuple(field_names) if field_names else tuple(f.name for f in ros_cloud.fields)
             if not (self.pointcloud_metadata or {}).get('has_intensity', False):
                 self.pointcloud_metadata = dict(self.pointcloud_metadata or {}, **get_pointcloud_metadata(names))
@@ -425,8 +445,9 @@ class PointcloudPreprocessorNode(Node):
             out, counts, plane, maps = ctx.pipeline_run_maps([desc], pcfg)
         else:
             out, counts, plane = ctx.pipeline_run([desc], pcfg)
-        ctx.check()
-        c = counts.cpu().numpy()
+        c = counts.cpu().numpy()                    # the one synchronisation of the pipeline
+        if c[_capi.CNT_STATUS] != 0:                # data-dependent device error (key range / capacity): raise it
+            ctx.check()
         n_out = int(c[_capi.CNT_OUTPUT])
         pos, inten = ctx.split_xyzi(out, n_out, want_intensity=bool(self.pointcloud_metadata.get('has_intensity')))
         cloud = o3d.PointCloud(self.o3d_device)
