@@ -79,7 +79,12 @@ static int run_pipeline(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_c
   const bool has_normals = cfg->normals_enable != 0;
   APC_REQUIRE(ctx, !has_normals || (maps && maps->normals_dev), "normals_enable needs maps.normals_dev");
   // first kernel = k_dedup_insert (it uses neither the epoch nor the counters): it does k_begin's work
-  static const bool fold_env = getenv("APC_NO_FOLD") == nullptr;   // A/B knob for profiles/
+  // APC_FOLD=1: fold k_begin into k_dedup_insert and the counters into k_rs_final (11 launches per C2 scan instead
+  // of 13).  OFF by default: interleaved A/B, 8 lanes, two runs each - 64.84 / 64.69 us per scan folded against
+  // 63.37 / 63.77 with the two one-CTA launches, and the same single-scan latency (0.133 ms): inside a captured
+  // graph the tiny launches cost less than what they take off the two big kernels' critical paths
+  // (profiles/r2ab_fold_lanes.json).
+  static const bool fold_env = []() { const char* e = getenv("APC_FOLD"); return e && atoi(e) != 0; }();
   const bool fold_begin = fold_env && cfg->filter.dedup_mode == APC_DEDUP_OPEN3D && n_total > 0;
   int rc = fold_begin ? apc_begin_folded(ctx) : apc_begin(ctx, s);
   if (rc) return rc;
