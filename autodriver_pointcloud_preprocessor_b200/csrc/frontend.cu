@@ -35,6 +35,7 @@ struct FrontendParams {
   uint64_t* scan_state;
   ApcCtrl* ctrl;
   uint32_t do_begin;      // k_dedup_insert is the first kernel of the call: CTA 0 does k_begin's work
+  uint32_t stream_in;     // k_frontend reads the input with evict-first loads (APC_STREAM_IN, A/B knob)
 };
 
 // ---- duplicate removal: 64-bit open-addressing slots {fingerprint:32 | lowest point index:32} -----
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(APC_TILE_THREADS) k_frontend(const __grid_cons
   const uint32_t epoch = prm.ctrl->epoch;
   TilePoint pt[APC_TILE_ITEMS];
   APC_STAMP(1, 0);
-  load_tile<GENERIC>(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt);
+  load_tile<GENERIC>(s, tile - s.tile_begin, prm.skip_nans != 0, stage, &bar, pt, prm.stream_in != 0);
 
   bool keep[APC_TILE_ITEMS];
   uint32_t gidx[APC_TILE_ITEMS];
@@ -500,6 +501,8 @@ int apc_frontend_nobegin(apc_ctx* ctx, const apc_cloud_desc* clouds, uint32_t n_
   const bool generic = smem != 0;   // some segment needs the byte-record decoder
   APC_REQUIRE(ctx, !ctx->fold_begin || prm.dedup, "folded begin needs the duplicate-insert kernel");
   prm.do_begin = ctx->fold_begin ? 1u : 0u;
+  static const uint32_t stream_in = []() { const char* e = getenv("APC_STREAM_IN"); return e ? (uint32_t)atoi(e) : 0u; }();
+  prm.stream_in = stream_in;
   if (prm.dedup) {
     APC_PROF(ctx, "k_dedup_insert", s);
     if (generic) apc_klaunch(ctx, k_dedup_insert<true>, prm.n_tiles, APC_TILE_THREADS, smem, s, prm);
