@@ -45,8 +45,8 @@ def launch_shares():
     total = sum(v[0] for v in ours.values())
     other = sum(v[0] for k, v in agg.items() if not k.startswith("k_"))
     with open(os.path.join(OUT, f"{tag}_launch_shares.csv"), "w") as f:
-        f.write(f"# ncu launch list of `python bench.py --steps 2 --warmup 3 --frames-total 16 --no-cpu-baseline --no-configs --no-e2e` ({tag})\n")
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 2500: cold-cache, serialised launches;\n")
+        f.write(f"# ncu launch list of the small bench command of profiles/gpu_final*.sh ({tag})\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: cold-cache, serialised launches;\n")
         f.write("# compare SHARES with bench.py's CUDA-event 'kernels' table, not absolute times.\n")
         f.write(f"# apc kernels {total / 1e3:.1f} us over {sum(v[1] for v in ours.values())} launches; "
                 f"other (torch copies / fills) {other / 1e3:.1f} us\n")
