@@ -4,6 +4,7 @@
 #include "apc_common.cuh"
 
 #define GRID_EMPTY 0xffffffffffffffffull
+#define GRID_CTR_CELLS 24     // ctrl->counters slot: occupied cells appended to GridDev::cells (zeroed by k_begin)
 #define GRID_NOSLOT 0xffffffffu
 // One cell of the open-addressing table: key, population and the start of its run in the sorted
 // array share one 16-byte slot, so a query resolves a cell with ONE 128-bit load (the key probe and
@@ -24,6 +25,9 @@ struct GridDev {
   float* cell;               // [levels] cell sizes (device)
   float cell0;               // > 0: single-level grid whose cell size the host knows (no k_grid_cells launch)
   float inv0;                // > 0: cell index = floor(x * inv0) instead of floor(x / cell0) (see grid_coord_g)
+  uint32_t* cells;           // != NULL: grid_insert_items appends the slot of every newly occupied cell (the point
+                             // that takes arrival rank 0) to this list, counted in ctrl->counters[GRID_CTR_CELLS]:
+                             // the run assignment then walks ~11 k cells instead of 205 k points (k_grid_assign_cells)
   uint32_t cursor_base;      // first ctrl->counters slot of this grid's per-level scatter cursors (the radius
                              // grid and the KNN grid can both be built inside one pipeline run)
 };
@@ -115,4 +119,9 @@ __device__ __forceinline__ void grid_insert_items(const GridDev& g, uint32_t lev
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j)
     if (slot[j] != GRID_NOSLOT) rank[j] = atomicAdd(&g.slots[slot[j]].fill, 1u);
+  if (g.cells) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (slot[j] != GRID_NOSLOT && rank[j] == 0u) g.cells[atomicAdd(&ctrl->counters[GRID_CTR_CELLS], 1u)] = slot[j];
+  }
 }

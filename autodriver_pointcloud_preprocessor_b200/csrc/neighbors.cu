@@ -142,6 +142,36 @@ k_grid_assign(uint32_t n_max, const uint32_t* n_dev, GridDev g, ApcCtrl* ctrl) {
   APC_STAMP(2, 1);
 }
 
+// The same over the LIST of occupied cells a producer kernel recorded while inserting (GridDev::cells): with
+// cells of 2r a voxelised scan occupies ~11 k cells, so this walks 18x fewer entries than the per-point pass.
+__global__ void __launch_bounds__(256) k_grid_assign_cells(GridDev g, ApcCtrl* ctrl, uint32_t n_max) {
+  pdl_enter();
+  const uint32_t nc = min(ctrl->counters[GRID_CTR_CELLS], n_max);
+  const uint32_t lane = lane_id();
+  for (uint32_t base = blockIdx.x * blockDim.x; base < nc; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t slot = GRID_NOSLOT, cnt = 0;
+    if (i < nc) {
+      slot = g.cells[i];
+      cnt = g.slots[slot].fill;
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t at = 0;
+    if (lane == 31 && total) {
+      at = atomicAdd(&ctrl->counters[g.cursor_base], total);
+      if (at + total > n_max) atomicOr(&ctrl->err, APC_DEVERR_CAPACITY);
+    }
+    at = __shfl_sync(0xffffffffu, at, 31);
+    if (cnt) g.slots[slot].start = at + incl - cnt;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_grid_scatter(const float4* __restrict__ pts, uint32_t n_max, const uint32_t* n_dev, GridDev g) {
   pdl_enter();
@@ -1012,6 +1042,7 @@ __global__ void k_grid_cells(const ApcCtrl* ctrl, float hint, uint32_t levels, f
 struct GridHost {
   GridDev d{};
   uint32_t cap = 0, n_alloc = 0;
+  uint32_t* cells_buf = nullptr;   // occupied-cell list of the single-level grid (handed out by apc_radius_grid_view)
 };
 
 struct NeighborScratch {
@@ -1030,7 +1061,7 @@ void apc_neighbors_release(apc_ctx* ctx) {
   NeighborScratch* s = ctx->neighbors;
   if (!s) return;
   for (auto& g : s->grid) {
-    void* ptrs[] = {g.d.slots, g.d.slot, g.d.rank, g.d.sorted, g.d.cell};
+    void* ptrs[] = {g.d.slots, g.d.slot, g.d.rank, g.d.sorted, g.d.cell, g.cells_buf};
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
@@ -1057,6 +1088,8 @@ int apc_neighbors_prepare(apc_ctx* ctx, int which) {
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.rank, (size_t)levels * M * sizeof(uint32_t)));
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.sorted, (size_t)levels * M * sizeof(float4)));
   APC_CUDA(ctx, cudaMalloc((void**)&g.d.cell, 16 * sizeof(float)));
+  g.cells_buf = nullptr;
+  if (which == 0) APC_CUDA(ctx, cudaMalloc((void**)&g.cells_buf, M * sizeof(uint32_t)));
   g.d.cap_mask = (uint32_t)cap - 1;
   g.d.levels = levels;
   g.d.cursor_base = which == 0 ? CTR_CURSOR_RADIUS : CTR_CURSOR;
@@ -1088,6 +1121,8 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
   }
   g.d.cell0 = (g.d.levels == 1 && cell_hint > 0.0f) ? cell_hint : 0.0f;
   g.d.inv0 = (reciprocal && g.d.cell0 > 0.0f) ? 1.0f / g.d.cell0 : 0.0f;
+  static const bool cell_list = getenv("APC_NO_CELL_LIST") == nullptr;   // A/B knob
+  g.d.cells = (inserted && cell_list) ? g.cells_buf : nullptr;
   if (!(g.d.cell0 > 0.0f)) k_grid_cells<<<1, 1, 0, s>>>(ctx->ctrl, cell_hint, g.d.levels, g.d.cell);
   const dim3 grid(bx, g.d.levels);
   if (!inserted) {   // (the pipeline's voxel stage inserts its centroids as it writes them)
@@ -1096,7 +1131,10 @@ static int grid_build(apc_ctx* ctx, GridHost& g, const float4* pts, uint32_t n_m
   }
   {
     APC_PROF(ctx, "k_grid_assign", s);
-    apc_klaunch(ctx, k_grid_assign, grid, 256, 0, s, n_max, n_dev, g.d, ctx->ctrl);
+    if (inserted && g.d.cells && g.d.levels == 1)   // the producer listed the occupied cells
+      apc_klaunch(ctx, k_grid_assign_cells, min(apc_div_up(n_max, 256), (uint32_t)APC_SM_COUNT), 256, 0, s, g.d, ctx->ctrl, n_max);
+    else
+      apc_klaunch(ctx, k_grid_assign, grid, 256, 0, s, n_max, n_dev, g.d, ctx->ctrl);
   }
   APC_PROF(ctx, "k_grid_scatter", s);
   apc_klaunch(ctx, k_grid_scatter, grid, 256, 0, s, pts, n_max, n_dev, g.d);
@@ -1193,6 +1231,7 @@ int apc_radius_grid_view(apc_ctx* ctx, double radius, GridDev* out) {
   GridHost& g = scratch_of(ctx)->grid[0];
   g.d.cell0 = radius_cell((float)radius);
   g.d.inv0 = radius_cell_mult() >= 2.0f ? 1.0f / g.d.cell0 : 0.0f;
+  g.d.cells = getenv("APC_NO_CELL_LIST") ? nullptr : g.cells_buf;   // the caller inserts: it also lists the occupied cells
   *out = g.d;
   return APC_OK;
 }
