@@ -381,7 +381,7 @@ __device__ __forceinline__ uint32_t radius_count_oct(const GridDev& g, float c, 
   return cnt;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_radius_query_oct(uint32_t n_max, const uint32_t* n_dev, GridDev g, float r, float r2, uint32_t nb_points, int need_counts,
                    uint8_t* __restrict__ mask, uint32_t* __restrict__ counts, const ApcCtrl* __restrict__ ctrl) {
   pdl_enter();
@@ -619,8 +619,11 @@ static int radius_decide(apc_ctx* ctx, const GridDev& g, uint32_t n_max, const u
     APC_PROF(ctx, "k_radius_query", s);
     if (coop_max)
       apc_klaunch(ctx, k_radius_decide_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, mask, ctx->ctrl, own_rounds, coop_max);
-    else
-      apc_klaunch(ctx, k_radius_query_oct, bq, 128, 0, s, n_max, n_dev, g, r, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    else {
+      static const uint32_t blk = []() { const char* e = getenv("APC_RADIUS_BLOCK"); const int v = e ? atoi(e) : 128; return (uint32_t)((v == 64 || v == 256) ? v : 128); }();
+      const uint32_t bqb = min(apc_div_up(n_max, blk), (uint32_t)APC_SM_COUNT * (2048u / blk));
+      apc_klaunch(ctx, k_radius_query_oct, bqb, blk, 0, s, n_max, n_dev, g, r, r2, nb_points, 0, mask, nullptr, ctx->ctrl);
+    }
     APC_LAUNCH_CHECK(ctx, "k_radius_query_oct");
     return APC_OK;
   }
