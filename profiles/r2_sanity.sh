@@ -1,1 +1,2 @@
-timeout 400 python -m pytest tests/test_gpu_knobs.py -m gpu -x -q 2>&1 | tail -4
+timeout 200 python bench.py --no-cpu-baseline --no-configs --frames-total 256 --steps 10 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['p50_latency_ms'], d['e2e']['value'], d['pipeline_roofline'])"
