@@ -1,2 +1,2 @@
-timeout 200 python bench.py --no-cpu-baseline --no-configs --frames-total 256 --steps 10 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['p50_latency_ms'], d['e2e']['value'], d['pipeline_roofline'])"
+O=gpurun_out; mkdir -p $O
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_knn_query --launch-skip 1 -c 1 -f -o $O/prof_knn_r2x python profiles/run_c4.py > $O/ncu_knn_r2x.log 2>&1; echo "rc=$?"
