@@ -51,7 +51,7 @@ from ._ros_compat import (HAVE_ROS, Buffer, ConnectivityException, Duration, Ext
                           LookupException, Node, Parameter, ParameterDescriptor, ParameterType, PointCloud2,
                           PointField, QoSHistoryPolicy, QoSProfile, QoSReliabilityPolicy, SetParametersResult,
                           Time, TransformListener, point_cloud2, rclpy, tf2_ros)
-from .utils import (raw_column, packed_message_bytes, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
+from .utils import (raw_column, packed_message_bytes, device_native_endian, FIELD_DTYPE_MAP, FIELD_DTYPE_MAP_INV, VENDOR_MAPPINGS, check_field,  # noqa: F401
                     convert_pointcloud_to_numpy, crop_pointcloud, dict_to_open3d_tensor_pointcloud,
                     extract_rgb_from_pointcloud, get_current_time, get_fields_from_dicts, get_pointcloud_metadata,
                     get_time_difference, numpy_struct_to_pointcloud2, pointcloud_to_dict, remove_duplicates,
@@ -310,7 +310,7 @@ class PointcloudPreprocessorNode(Node):
         n_bytes = ros_cloud.width * ros_cloud.height * ros_cloud.point_step
         tight = int(getattr(ros_cloud, 'row_step', 0) or 0) in (0, ros_cloud.width * ros_cloud.point_step)
         if n_bytes == 0 or not tight or len(ros_cloud.data) < n_bytes:
-            return packed_message_bytes(ros_cloud).cuda()
+            return device_native_endian(packed_message_bytes(ros_cloud).cuda(), ros_cloud)
         stage = getattr(self, '_pinned_in', None)
         if stage is None or stage.numel() < n_bytes:
             cap = max(n_bytes + n_bytes // 4, 1 << 20)
@@ -319,7 +319,7 @@ class PointcloudPreprocessorNode(Node):
         stage.numpy()[:n_bytes] = np.frombuffer(ros_cloud.data, dtype=np.uint8, count=n_bytes)
         dev = self._dev_in[:n_bytes]
         dev.copy_(stage[:n_bytes], non_blocking=True)
-        return dev
+        return device_native_endian(dev, ros_cloud)       # a no-op unless the message is big-endian
 
     def extract_pointcloud(self, ros_cloud):
         """pp.py:394-445: message -> device-resident carrier.  Returns None on every path, like

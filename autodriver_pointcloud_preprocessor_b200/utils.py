@@ -139,6 +139,29 @@ def packed_message_bytes(ros_cloud):
     return raw
 
 
+def is_foreign_endian(ros_cloud) -> bool:
+    """read_points byte-swaps the records when the message's endianness differs from the host's
+    (sensor_msgs_py.point_cloud2.read_points)."""
+    return bool(sys.byteorder != 'little') != bool(ros_cloud.is_bigendian)
+
+
+def device_native_endian(data_dev, ros_cloud):
+    """Byte-swap every multi-byte field of the uploaded records IN PLACE on the device so that the kernels
+    (which read native little-endian fields) see what ``read_points`` would return.  Off the hot path:
+    sensors publish little-endian; a handful of strided device copies per message."""
+    n = ros_cloud.width * ros_cloud.height
+    if n == 0 or not is_foreign_endian(ros_cloud):
+        return data_dev
+    rows = data_dev[:n * ros_cloud.point_step].view(n, ros_cloud.point_step)
+    for f in ros_cloud.fields:
+        size = np.dtype(FIELD_DTYPE_MAP[f.datatype]).itemsize
+        for c in range(max(1, int(getattr(f, 'count', 1) or 1))):
+            a = f.offset + c * size
+            if size > 1:
+                rows[:, a:a + size] = rows[:, a:a + size].flip(1)
+    return data_dev
+
+
 def raw_column(rows, field):
     """One field of every record of a device byte buffer viewed as ``[n, point_step]``: a contiguous
     device tensor of the field's own dtype (the per-field slice ``read_points`` returns)."""
@@ -173,13 +196,11 @@ def pointcloud_to_dict(ros_cloud, field_names=None, skip_nans=True, organize_clo
     metadata_dict['num_fields'] = len(names)
     if not metadata_dict.get('has_intensity', False):
         metadata_dict.update(get_pointcloud_metadata(metadata_dict['field_names']))
-    if bool(sys.byteorder != 'little') != bool(ros_cloud.is_bigendian):
-        raise NotImplementedError("big-endian PointCloud2 buffers are not supported by the CUDA unpack")
     n = ros_cloud.width * ros_cloud.height
-    if _data_dev is not None:              # the node uploads the message once and shares the buffer
+    if _data_dev is not None:              # the node uploads the message once (already in native byte order) and shares the buffer
         data = _data_dev
     else:
-        data = packed_message_bytes(ros_cloud).cuda()
+        data = device_native_endian(packed_message_bytes(ros_cloud).cuda(), ros_cloud)
     ctx = geometry.get_context(n)
     desc = engine.make_cloud_desc(ros_cloud.fields, ros_cloud.point_step, n, data, field_names=field_names)
     cfg = engine.make_filter_cfg(skip_nans=bool(skip_nans and not ros_cloud.is_dense))

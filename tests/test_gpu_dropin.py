@@ -35,6 +35,42 @@ def test_pointcloud_to_dict_matches_reference_conversion():
             assert np.array_equal(got, ref[k], equal_nan=True), (layout, k)
 
 
+def test_big_endian_message_is_byte_swapped_like_read_points():
+    """read_points byte-swaps a message whose endianness differs from the host's (utils.py:206-211): the same
+    records stored big-endian give the same carrier tensors, and the node publishes the same cloud."""
+    from autodriver_pointcloud_preprocessor_b200 import utils
+    from oracle import pc2
+    for layout in ("xyzirt22", "ouster48"):
+        scan, msg = scan_msg(layout, seed=57, n_beams=16, n_az=256)
+        le = np.frombuffer(msg.data, dtype=pc2.dtype_from_fields(msg.fields, msg.point_step))
+        be_dtype = np.dtype({"names": list(le.dtype.names), "formats": [le.dtype[n].newbyteorder(">") for n in le.dtype.names],
+                             "offsets": [le.dtype.fields[n][1] for n in le.dtype.names], "itemsize": le.dtype.itemsize})
+        be = np.zeros(le.shape, dtype=be_dtype)
+        for name in le.dtype.names:
+            be[name] = le[name]
+        import copy
+        msg_be = copy.copy(msg)
+        msg_be.data, msg_be.is_bigendian = be.tobytes(), True
+        assert msg_be.data != msg.data
+        a, _ = utils.pointcloud_to_dict(msg, None, True, False, None)
+        b, _ = utils.pointcloud_to_dict(msg_be, None, True, False, None)
+        assert a.keys() == b.keys()
+        for k in a:
+            if k != "header":
+                x, y = a[k].cpu().numpy(), b[k].cpu().numpy()
+                assert x.dtype == y.dtype and x.tobytes() == y.tobytes(), (layout, k)
+        ref, _ = pc2.pointcloud_to_dict(msg_be, None, True, False, None)          # the oracle runs read_points' byteswap
+        assert np.array_equal(b["positions"].cpu().numpy().view(np.uint32), ref["positions"].view(np.uint32))
+        outs = []
+        for m in (msg, msg_be):
+            node = make_node({"use_gpu": True, "voxel_size": 0.2, "estimate_normals": False, "remove_ground": True,
+                              "remove_ground.seed": 3})
+            node.callback(m)
+            assert len(node.pointcloud_pub.messages) == 1, "callback dropped the frame"
+            outs.append(bytes(node.pointcloud_pub.messages[0].data))
+        assert outs[0] == outs[1]
+
+
 def test_carrier_ops_against_oracle(golden_dir):
     from autodriver_pointcloud_preprocessor_b200 import geometry as o3d
     from autodriver_pointcloud_preprocessor_b200 import utils
